@@ -1,0 +1,1096 @@
+/*
+ * ehm_oracle.c -- CPU restatement (plain C, fp64) of the explicit hybrid MPC partitioning
+ * oracle + ECC/L-CSS recursion.  See ehm_oracle.h for the scope, the list of restated
+ * reference functions (file:line) and the "parity unpinned" statement.
+ *
+ * TEST INFRASTRUCTURE ONLY -- never linked into, imported by or called from the product.
+ *
+ * Algorithm in one paragraph.  The reference's MICPs range over binary commutations delta with
+ * sum_i z[k][i]==1 (lib/mpc_library.py:526-527), i.e. over K^N one-hot mode sequences
+ * ("candidates").  For a fixed candidate the active big-M pair (:530-534) is an equality, so
+ * the states are affine in (theta,u) and every oracle problem condenses to a small dense
+ * convex QP/LP in u (and, for the simplex problems of lib/oracle.py:70-102, in the
+ * barycentric coordinates beta of theta and one epigraph variable).  MOSEK's branch & bound
+ * is replaced by explicit enumeration with the canonical selection rules written next to each
+ * function below.  Each convex sub-problem is solved by a dense Mehrotra predictor-corrector
+ * interior-point method after an always-feasible "phase-1" LP decided feasibility.
+ */
+#include "ehm_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#define MAXNV 40
+
+static long g_iters = 0;
+long ehmo_total_iters(void) { return g_iters; }
+static inline double fmax2(double a, double b) { return a > b ? a : b; }
+
+struct ehmo_problem {
+    int n, nu, N, K, p;
+    int U, m, ncand, Y;          /* U = N*nu inputs, m = N*p rows, Y = U+n+1 */
+    double *A, *B, *w, *C, *D, *e, *Q, *P, *R, *ru, *tscale;
+    double eps_a, eps_r;
+    double *cG, *cS, *cg, *cM, *crho; /* condensed data of every candidate */
+    long nsolves;
+};
+
+/* ------------------------------------------------------------------------------------ */
+/* small dense helpers                                                                  */
+/* ------------------------------------------------------------------------------------ */
+static double *dalloc(size_t k) { return (double *)calloc(k ? k : 1, sizeof(double)); }
+
+static double *dcopy(const double *src, size_t k)
+{
+    double *d = dalloc(k);
+    memcpy(d, src, k * sizeof(double));
+    return d;
+}
+
+/* in-place lower Cholesky of the nv x nv SPD matrix K (row-major).  A pivot that collapses
+ * below 1e-13 of its own original diagonal entry (rank-deficient normal matrix close to an LP
+ * vertex) is replaced by a huge one, which freezes that direction for this Newton step
+ * (the classical LIPSOL safeguard).  returns 0 on success, 1 on NaN/Inf. */
+static int cholesky(int nv, double *K)
+{
+    double maxd = 0;
+    for (int j = 0; j < nv; ++j) maxd = fmax2(maxd, K[j * nv + j]);
+    if (!isfinite(maxd) || !(maxd > 0.0)) return 1;
+    for (int j = 0; j < nv; ++j) {
+        const double d0 = K[j * nv + j];
+        double d = d0;
+        for (int k = 0; k < j; ++k) d -= K[j * nv + k] * K[j * nv + k];
+        if (!isfinite(d)) return 1;
+        if (d <= 1e-13 * d0 || d0 <= 0.0) d = 1e100;
+        d = sqrt(d);
+        K[j * nv + j] = d;
+        for (int i = j + 1; i < nv; ++i) {
+            double v = K[i * nv + j];
+            for (int k = 0; k < j; ++k) v -= K[i * nv + k] * K[j * nv + k];
+            K[i * nv + j] = v / d;
+        }
+    }
+    return 0;
+}
+
+static void chol_solve(int nv, const double *L, double *b)
+{
+    for (int i = 0; i < nv; ++i) {
+        double v = b[i];
+        for (int k = 0; k < i; ++k) v -= L[i * nv + k] * b[k];
+        b[i] = v / L[i * nv + i];
+    }
+    for (int i = nv - 1; i >= 0; --i) {
+        double v = b[i];
+        for (int k = i + 1; k < nv; ++k) v -= L[k * nv + i] * b[k];
+        b[i] = v / L[i * nv + i];
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Dense Mehrotra predictor-corrector for  min 0.5 z'Hz + f'z  s.t.  G z <= h           */
+/* (what CVXPY->MOSEK does for the reference at every .solve(), lib/oracle.py:131-378)   */
+/* z0 != NULL gives the primal start (slacks max(h-Gz0,1)).  returns 0 converged,        */
+/* 1 iteration limit, 2 factorisation breakdown.                                         */
+/* ------------------------------------------------------------------------------------ */
+static int qp_solve(int nv, int m, const double *H, const double *f, const double *G,
+                    const double *h, const double *z0, double *z, double *obj_out,
+                    int *iters_out)
+{
+    double *s = dalloc(m), *lam = dalloc(m), *rp = dalloc(m), *ds = dalloc(m),
+           *dl = dalloc(m), *rc = dalloc(m), *wv = dalloc(m);
+    double K[MAXNV * MAXNV], rd[MAXNV], dz[MAXNV], rhs[MAXNV];
+    int status = 1, it = 0;
+    double rho = 1.0, rd0 = 0.0; /* exact-arithmetic dual residual = rho * rd0 (see below) */
+    double fmax = 0, obj = 0;
+    for (int j = 0; j < nv; ++j) fmax = fmax2(fmax, fabs(f[j]));
+    for (int j = 0; j < nv; ++j) z[j] = z0 ? z0[j] : 0.0;
+    for (int r = 0; r < m; ++r) {
+        double gz = 0;
+        for (int j = 0; j < nv; ++j) gz += G[r * nv + j] * z[j];
+        s[r] = fmax2(h[r] - gz, 1.0);
+        lam[r] = 1.0 / s[r]; /* centred start: s.lam = 1 on every row */
+    }
+    for (it = 0; it <= EHMO_MAX_ITER; ++it) {
+        double rpmax = 0, rdmax = 0, mu = 0;
+        obj = 0;
+        for (int j = 0; j < nv; ++j) {
+            double v = f[j], hz = 0;
+            if (H)
+                for (int k = 0; k < nv; ++k) hz += H[j * nv + k] * z[k];
+            obj += z[j] * (f[j] + 0.5 * hz);
+            rd[j] = v + hz;
+        }
+        for (int r = 0; r < m; ++r) {
+            double gz = 0;
+            for (int j = 0; j < nv; ++j) {
+                gz += G[r * nv + j] * z[j];
+                rd[j] += G[r * nv + j] * lam[r];
+            }
+            rp[r] = gz + s[r] - h[r];
+            rpmax = fmax2(rpmax, fabs(rp[r]));
+            mu += s[r] * lam[r];
+        }
+        for (int j = 0; j < nv; ++j) rdmax = fmax2(rdmax, fabs(rd[j]));
+        double zmax = 0, lmax = 0;
+        for (int j = 0; j < nv; ++j) zmax = fmax2(zmax, fabs(z[j]));
+        for (int r = 0; r < m; ++r) lmax = fmax2(lmax, lam[r]);
+        if (!isfinite(mu) || !isfinite(rdmax) || !isfinite(rpmax)) { status = 2; break; }
+        if (getenv("EHMO_DEBUG")) fprintf(stderr, "it %d rp %.3e rd %.3e mu %.3e obj %.10g lmax %.3e zmax %.3e\n", it, rpmax, rdmax, mu, obj, lmax, zmax);
+        /* residuals relative to the magnitude of the terms they are made of (rows are
+         * normalised, |G| <= 1): |Gz| <= |z|, |G'lam| <= |lam| */
+        if (it == 0) rd0 = rdmax;
+        /* Every step scales the dual residual by exactly (1 - alpha (1 - sigma)); the value
+         * measured above additionally carries the round-off of the normal equations (up to
+         * ~1e-4 relative once lam/s spans 20+ orders), so convergence is tested on the
+         * propagated value rho*rd0 and the measured one only as a coarse guard. */
+        if (rpmax <= EHMO_TOL_IPM * (1 + zmax) && rho * rd0 <= EHMO_TOL_IPM * (1 + fmax + lmax) &&
+            rdmax <= EHMO_TOL_DUAL * (1 + fmax + lmax) &&
+            mu <= EHMO_TOL_IPM * (1 + fabs(obj))) {
+            status = 0;
+            break;
+        }
+        if (it == EHMO_MAX_ITER) break;
+        mu /= m;
+        /* K = H + G' diag(lam/s) G */
+        for (int j = 0; j < nv * nv; ++j) K[j] = H ? H[j] : 0.0;
+        for (int r = 0; r < m; ++r) {
+            double wr = lam[r] / s[r];
+            wv[r] = wr;
+            const double *g = G + r * nv;
+            for (int j = 0; j < nv; ++j) {
+                double gj = wr * g[j];
+                if (gj == 0.0) continue;
+                for (int k = 0; k <= j; ++k) K[j * nv + k] += gj * g[k];
+            }
+        }
+        for (int j = 0; j < nv; ++j)
+            for (int k = j + 1; k < nv; ++k) K[j * nv + k] = K[k * nv + j];
+        if (cholesky(nv, K)) { status = 2; break; }
+        double alpha = 1.0, resc = 1.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            /* pass 0: affine predictor (rc = s.lam); pass 1: centring + second-order corrector
+             * with sigma = (1-alpha_aff)^3 and the residuals scaled by (1-sigma), so that
+             * infeasibility and complementarity shrink at the same rate (the CVXOPT/ECOS form
+             * of Mehrotra's method; the plain form cycles on thin feasible sets). */
+            if (pass == 0) {
+                for (int r = 0; r < m; ++r) rc[r] = s[r] * lam[r];
+            } else {
+                double sig = (1.0 - alpha) * (1.0 - alpha) * (1.0 - alpha);
+                resc = 1.0 - sig;
+                for (int r = 0; r < m; ++r) rc[r] = s[r] * lam[r] + ds[r] * dl[r] - sig * mu;
+            }
+            for (int j = 0; j < nv; ++j) rhs[j] = -resc * rd[j];
+            for (int r = 0; r < m; ++r) {
+                double t = (-rc[r] + lam[r] * resc * rp[r]) / s[r];
+                const double *g = G + r * nv;
+                for (int j = 0; j < nv; ++j) rhs[j] -= g[j] * t;
+            }
+            chol_solve(nv, K, rhs);
+            memcpy(dz, rhs, nv * sizeof(double));
+            double amax = 1e300;
+            for (int r = 0; r < m; ++r) {
+                double gdz = 0;
+                const double *g = G + r * nv;
+                for (int j = 0; j < nv; ++j) gdz += g[j] * dz[j];
+                ds[r] = -resc * rp[r] - gdz;
+                dl[r] = (-rc[r] - lam[r] * ds[r]) / s[r];
+                if (ds[r] < 0) amax = fmin(amax, -s[r] / ds[r]);
+                if (dl[r] < 0) amax = fmin(amax, -lam[r] / dl[r]);
+            }
+            alpha = (pass == 0) ? fmin(1.0, amax) : fmin(1.0, 0.99 * amax);
+        }
+        {
+            static double gam = -1;
+            if (gam < 0) gam = getenv("EHMO_GAMMA") ? atof(getenv("EHMO_GAMMA")) : 0.0;
+            if (gam > 0) {
+                for (int tries = 0; tries < 20; ++tries) {
+                    double mun = 0, mn = 1e300;
+                    for (int r = 0; r < m; ++r) {
+                        double pr = (s[r] + alpha * ds[r]) * (lam[r] + alpha * dl[r]);
+                        mun += pr;
+                        mn = fmin(mn, pr);
+                    }
+                    if (mn >= gam * mun / m) break;
+                    alpha *= 0.8;
+                }
+            }
+        }
+        g_iters++;
+        rho *= 1.0 - alpha * resc;
+        if (getenv("EHMO_DEBUG")) {
+            double mn = 1e300, mx = 0; int imn = -1;
+            for (int r = 0; r < m; ++r) { double pr = s[r] * lam[r]; if (pr < mn) { mn = pr; imn = r; } if (pr > mx) mx = pr; }
+            fprintf(stderr, "    alpha %.3e  min s.lam %.3e (row %d s %.3e lam %.3e) max %.3e mu %.3e\n", alpha, mn, imn, s[imn], lam[imn], mx, mu);
+        }
+        for (int j = 0; j < nv; ++j) z[j] += alpha * dz[j];
+        for (int r = 0; r < m; ++r) {
+            s[r] += alpha * ds[r];
+            lam[r] += alpha * dl[r];
+        }
+    }
+    *obj_out = obj;
+    if (status != 0 && getenv("EHMO_FAILTRACE")) {
+        double rpm = 0, rdm = 0, mu = 0;
+        for (int r = 0; r < m; ++r) { rpm = fmax2(rpm, fabs(rp[r])); mu += s[r] * lam[r]; }
+        for (int j = 0; j < nv; ++j) rdm = fmax2(rdm, fabs(rd[j]));
+        fprintf(stderr, "FAIL status %d nv %d m %d it %d rp %.3e rd %.3e mu %.3e obj %.6g hmax %.3e fmax %.3e\n", status, nv, m, it, rpm, rdm, mu / m, obj, 0.0, fmax);
+    }
+    if (iters_out) *iters_out = it;
+    free(s); free(lam); free(rp); free(ds); free(dl); free(rc); free(wv);
+    return status;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Row preparation: drop constant rows (checked, closed tolerance), normalise the rest.   */
+/* rho[r] is the row's natural scale in (u,theta) space (used only to make the            */
+/* constant-row test scale-free).  returns number of kept rows, or -1 if a constant row   */
+/* is violated (problem infeasible).                                                      */
+/* ------------------------------------------------------------------------------------ */
+static int prep_rows(int nv, int m, const double *G, const double *h, const double *rho,
+                     double *Go, double *ho)
+{
+    int mo = 0;
+    for (int r = 0; r < m; ++r) {
+        double nrm = 0;
+        for (int j = 0; j < nv; ++j) nrm = fmax2(nrm, fabs(G[r * nv + j]));
+        double sc = rho[r] > 0 ? rho[r] : 1.0;
+        if (nrm <= EHMO_ZERO_ROW * sc) {
+            if (h[r] < -EHMO_TAU_CONST * sc) return -1;
+            continue;
+        }
+        double inv = 1.0 / nrm;
+        for (int j = 0; j < nv; ++j) Go[mo * nv + j] = G[r * nv + j] * inv;
+        ho[mo] = h[r] * inv;
+        ++mo;
+    }
+    return mo;
+}
+
+/* phase 1:  min sigma  s.t.  G z - sigma <= h  (rows already normalised).
+ * returns 1 alive (sigma* <= -TAU_INT), 0 not alive, <0 solver failure. */
+static int phase1(ehmo_problem *pb, int nv, int m, const double *G, const double *h,
+                  double *sigma_out)
+{
+    int na = nv + 1;
+    double *Ga = dalloc((size_t)m * na);
+    double f[MAXNV], z0[MAXNV], z[MAXNV], obj;
+    double s0 = 0;
+    for (int r = 0; r < m; ++r) {
+        memcpy(Ga + (size_t)r * na, G + (size_t)r * nv, nv * sizeof(double));
+        Ga[(size_t)r * na + nv] = -1.0;
+        s0 = fmax2(s0, -h[r]);
+    }
+    for (int j = 0; j < nv; ++j) { f[j] = 0; z0[j] = 0; }
+    f[nv] = 1.0;
+    z0[nv] = s0 + 1.0; /* strictly feasible start: slacks h+sigma >= 1 */
+    int st = qp_solve(na, m, NULL, f, Ga, h, z0, z, &obj, NULL);
+    __sync_fetch_and_add(&pb->nsolves, 1);
+    free(Ga);
+    if (sigma_out) *sigma_out = obj;
+    if (st != 0) return -1;
+    return obj <= -EHMO_TAU_INT ? 1 : 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Condensation of one candidate (mode sequence)                                          */
+/* ------------------------------------------------------------------------------------ */
+static void seq_of(const ehmo_problem *pb, int c, int *seq)
+{
+    for (int k = pb->N - 1; k >= 0; --k) { seq[k] = c % pb->K; c /= pb->K; }
+}
+
+static void condense(ehmo_problem *pb, int c)
+{
+    const int n = pb->n, nu = pb->nu, N = pb->N, p = pb->p, U = pb->U, Y = pb->Y, m = pb->m;
+    int seq[64];
+    seq_of(pb, c, seq);
+    double *G = pb->cG + (size_t)c * m * U, *S = pb->cS + (size_t)c * m * n,
+           *g = pb->cg + (size_t)c * m, *M = pb->cM + (size_t)c * Y * Y,
+           *rho = pb->crho + (size_t)c * m;
+    /* T (n x Y): x_k = T [u; theta; 1] */
+    double *T = dalloc((size_t)n * Y), *Tn = dalloc((size_t)n * Y), *WT = dalloc((size_t)n * Y);
+    for (int i = 0; i < n; ++i) T[i * Y + U + i] = 1.0;
+    memset(M, 0, sizeof(double) * Y * Y);
+    for (int k = 0; k < N; ++k) {
+        const int i = seq[k];
+        const double *Ci = pb->C + (size_t)i * p * n, *Di = pb->D + (size_t)i * p * nu,
+                     *ei = pb->e + (size_t)i * p, *Ai = pb->A + (size_t)i * n * n,
+                     *Bi = pb->B + (size_t)i * n * nu, *wi = pb->w + (size_t)i * n;
+        for (int r = 0; r < p; ++r) {
+            const int row = k * p + r;
+            double *Gr = G + (size_t)row * U, *Sr = S + (size_t)row * n;
+            for (int j = 0; j < U; ++j) {
+                double v = 0;
+                for (int a = 0; a < n; ++a) v += Ci[r * n + a] * T[a * Y + j];
+                Gr[j] = v;
+            }
+            for (int j = 0; j < nu; ++j) Gr[k * nu + j] += Di[r * nu + j];
+            double gc = ei[r], nat = 0;
+            for (int j = 0; j < n; ++j) {
+                double v = 0;
+                for (int a = 0; a < n; ++a) v += Ci[r * n + a] * T[a * Y + U + j];
+                Sr[j] = -v;
+                nat = fmax2(nat, fabs(v) * pb->tscale[j]);
+            }
+            for (int a = 0; a < n; ++a) gc -= Ci[r * n + a] * T[a * Y + Y - 1];
+            g[row] = gc;
+            for (int j = 0; j < U; ++j) nat = fmax2(nat, fabs(Gr[j]));
+            rho[row] = nat;
+        }
+        /* input cost u_k' R u_k + ru' u_k */
+        for (int a = 0; a < nu; ++a) {
+            for (int b = 0; b < nu; ++b) M[(k * nu + a) * Y + k * nu + b] += pb->R[a * nu + b];
+            M[(k * nu + a) * Y + Y - 1] += 0.5 * pb->ru[i * nu + a];
+            M[(Y - 1) * Y + k * nu + a] += 0.5 * pb->ru[i * nu + a];
+        }
+        /* x_{k+1} = A x_k + B u_k + w */
+        for (int a = 0; a < n; ++a)
+            for (int j = 0; j < Y; ++j) {
+                double v = 0;
+                for (int b = 0; b < n; ++b) v += Ai[a * n + b] * T[b * Y + j];
+                Tn[a * Y + j] = v;
+            }
+        for (int a = 0; a < n; ++a) {
+            for (int j = 0; j < nu; ++j) Tn[a * Y + k * nu + j] += Bi[a * nu + j];
+            Tn[a * Y + Y - 1] += wi[a];
+        }
+        memcpy(T, Tn, sizeof(double) * n * Y);
+        /* state cost on x_{k+1}: Q for k+1<N, P for k+1==N (mpc_library.py:515-517) */
+        const double *W = (k + 1 < N) ? pb->Q : pb->P;
+        for (int a = 0; a < n; ++a)
+            for (int j = 0; j < Y; ++j) {
+                double v = 0;
+                for (int b = 0; b < n; ++b) v += W[a * n + b] * T[b * Y + j];
+                WT[a * Y + j] = v;
+            }
+        for (int i2 = 0; i2 < Y; ++i2)
+            for (int j = 0; j < Y; ++j) {
+                double v = 0;
+                for (int a = 0; a < n; ++a) v += T[a * Y + i2] * WT[a * Y + j];
+                M[i2 * Y + j] += v;
+            }
+    }
+    free(T); free(Tn); free(WT);
+}
+
+ehmo_problem *ehmo_create(int n, int nu, int N, int K, int p, const double *A, const double *B,
+                          const double *w, const double *C, const double *D, const double *e,
+                          const double *Q, const double *P, const double *R, const double *ru,
+                          const double *theta_scale, double eps_a, double eps_r)
+{
+    ehmo_problem *pb = (ehmo_problem *)calloc(1, sizeof(*pb));
+    pb->n = n; pb->nu = nu; pb->N = N; pb->K = K; pb->p = p;
+    pb->U = N * nu; pb->m = N * p; pb->Y = pb->U + n + 1;
+    if (pb->U + n + 2 > MAXNV || N > 60) { free(pb); return NULL; }
+    long nc = 1;
+    for (int k = 0; k < N; ++k) nc *= K;
+    pb->ncand = (int)nc;
+    pb->A = dcopy(A, (size_t)K * n * n); pb->B = dcopy(B, (size_t)K * n * nu);
+    pb->w = dcopy(w, (size_t)K * n); pb->C = dcopy(C, (size_t)K * p * n);
+    pb->D = dcopy(D, (size_t)K * p * nu); pb->e = dcopy(e, (size_t)K * p);
+    pb->Q = dcopy(Q, (size_t)n * n); pb->P = dcopy(P, (size_t)n * n);
+    pb->R = dcopy(R, (size_t)nu * nu); pb->ru = dcopy(ru, (size_t)K * nu);
+    pb->tscale = dcopy(theta_scale, n);
+    pb->eps_a = eps_a; pb->eps_r = eps_r;
+    pb->cG = dalloc((size_t)nc * pb->m * pb->U); pb->cS = dalloc((size_t)nc * pb->m * n);
+    pb->cg = dalloc((size_t)nc * pb->m); pb->cM = dalloc((size_t)nc * pb->Y * pb->Y);
+    pb->crho = dalloc((size_t)nc * pb->m);
+    for (int c = 0; c < pb->ncand; ++c) condense(pb, c);
+    return pb;
+}
+
+void ehmo_destroy(ehmo_problem *pb)
+{
+    if (!pb) return;
+    free(pb->A); free(pb->B); free(pb->w); free(pb->C); free(pb->D); free(pb->e);
+    free(pb->Q); free(pb->P); free(pb->R); free(pb->ru); free(pb->tscale);
+    free(pb->cG); free(pb->cS); free(pb->cg); free(pb->cM); free(pb->crho);
+    free(pb);
+}
+
+void ehmo_set_eps(ehmo_problem *pb, double eps_a, double eps_r)
+{
+    pb->eps_a = eps_a;
+    pb->eps_r = eps_r;
+}
+int ehmo_num_candidates(const ehmo_problem *pb) { return pb->ncand; }
+long ehmo_solve_count(const ehmo_problem *pb) { return pb->nsolves; }
+
+/* ------------------------------------------------------------------------------------ */
+/* P_theta_delta (lib/oracle.py:141-173): fixed-commutation convex QP at one theta.       */
+/* ------------------------------------------------------------------------------------ */
+int ehmo_p_theta_delta(ehmo_problem *pb, const double *theta, int c, double *J, double *u0)
+{
+    const int n = pb->n, U = pb->U, m = pb->m, Y = pb->Y;
+    if (c < 0 || c >= pb->ncand) return 0; /* not one-hot: sum(z[k])==1 violated */
+    const double *G = pb->cG + (size_t)c * m * U, *S = pb->cS + (size_t)c * m * n,
+                 *g = pb->cg + (size_t)c * m, *M = pb->cM + (size_t)c * Y * Y,
+                 *rho = pb->crho + (size_t)c * m;
+    double *h = dalloc(m), *Gn = dalloc((size_t)m * U), *hn = dalloc(m);
+    int ret = 0;
+    for (int r = 0; r < m; ++r) {
+        double v = g[r];
+        for (int j = 0; j < n; ++j) v += S[r * n + j] * theta[j];
+        h[r] = v;
+    }
+    int mo = prep_rows(U, m, G, h, rho, Gn, hn);
+    if (mo >= 0) {
+        int alive = phase1(pb, U, mo, Gn, hn, NULL);
+        if (alive < 0) ret = -1;
+        else if (alive == 1) {
+            double H[MAXNV * MAXNV], f[MAXNV], z[MAXNV], obj, cst;
+            for (int i = 0; i < U; ++i) {
+                for (int j = 0; j < U; ++j) H[i * U + j] = 2.0 * M[i * Y + j];
+                double v = M[i * Y + Y - 1];
+                for (int j = 0; j < n; ++j) v += M[i * Y + U + j] * theta[j];
+                f[i] = 2.0 * v;
+            }
+            cst = M[(Y - 1) * Y + Y - 1];
+            for (int i = 0; i < n; ++i) {
+                cst += 2.0 * M[(U + i) * Y + Y - 1] * theta[i];
+                for (int j = 0; j < n; ++j) cst += theta[i] * M[(U + i) * Y + U + j] * theta[j];
+            }
+            double cs = 1.0;
+            for (int i = 0; i < U; ++i) cs = fmax2(cs, fmax2(fabs(H[i * U + i]), fabs(f[i])));
+            for (int i = 0; i < U; ++i) {
+                f[i] /= cs;
+                for (int j = 0; j < U; ++j) H[i * U + j] /= cs;
+            }
+            int st = qp_solve(U, mo, H, f, Gn, hn, NULL, z, &obj, NULL);
+            obj *= cs;
+            __sync_fetch_and_add(&pb->nsolves, 1);
+            if (st == 0) {
+                ret = 1;
+                if (J) *J = obj + cst;
+                if (u0)
+                    for (int j = 0; j < pb->nu; ++j) u0[j] = z[j];
+            } else ret = -1;
+        }
+    }
+    free(h); free(Gn); free(hn);
+    return ret;
+}
+
+/* P_theta (lib/oracle.py:104-139): MICP = min over commutations.
+ * Canonical rule: argmin_c J_c(theta), ties -> smallest candidate index. */
+int ehmo_p_theta(ehmo_problem *pb, const double *theta, double *J, double *u0)
+{
+    int best = -1;
+    double Jb = 0, ub[MAXNV], Jc, uc[MAXNV];
+    for (int c = 0; c < pb->ncand; ++c) {
+        if (ehmo_p_theta_delta(pb, theta, c, &Jc, uc) == 1 && (best < 0 || Jc < Jb)) {
+            best = c; Jb = Jc;
+            memcpy(ub, uc, sizeof(double) * pb->nu);
+        }
+    }
+    if (best >= 0) {
+        if (J) *J = Jb;
+        if (u0) memcpy(u0, ub, sizeof(double) * pb->nu);
+    }
+    return best;
+}
+
+/* V_R (lib/oracle.py:175-218): a commutation feasible at every vertex of R, plus the vertex
+ * inputs/costs under it.  The reference takes whichever delta MOSEK returns for objective 0
+ * and blacklists it if a vertex QP then fails (:198-218).
+ * Canonical rule: among candidates whose P_theta_delta is feasible and converges at all n+1
+ * vertices, the one minimising sum_i J_c(v_i); ties -> smallest candidate index. */
+int ehmo_v_r(ehmo_problem *pb, const double *R, double *Jv, double *Uv)
+{
+    const int n = pb->n, nu = pb->nu;
+    int best = -1;
+    double sb = 0, Jc[MAXNV], Uc[MAXNV * MAXNV];
+    for (int c = 0; c < pb->ncand; ++c) {
+        int ok = 1;
+        double sum = 0;
+        for (int i = 0; i <= n && ok; ++i) {
+            ok = ehmo_p_theta_delta(pb, R + i * n, c, &Jc[i], Uc + i * nu) == 1;
+            sum += Jc[i];
+        }
+        if (ok && (best < 0 || sum < sb)) {
+            best = c; sb = sum;
+            memcpy(Jv, Jc, sizeof(double) * (n + 1));
+            memcpy(Uv, Uc, sizeof(double) * (n + 1) * nu);
+        }
+    }
+    return best;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Simplex problems (theta = v0 + E beta, beta >= 0, sum beta <= 1; lib/oracle.py:70-74)  */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    int nv, m;           /* nv = U+n (+1 with tau) */
+    double *G, *h, *rho; /* un-normalised rows */
+    double H[MAXNV * MAXNV], f[MAXNV], cst;
+    double cs; /* objective/tau scale: reported value = cs * obj + cst */
+} simplex_qp;
+
+/* build rows + cost of candidate c over simplex R in variables [u; beta] (with_tau=0) or
+ * [u; beta; tau] with the two epigraph rows of the eps-suboptimality test (with_tau=1). */
+static void build_simplex_qp(const ehmo_problem *pb, int c, const double *R, const double *Vr,
+                             int with_tau, simplex_qp *q)
+{
+    const int n = pb->n, U = pb->U, m = pb->m, Y = pb->Y;
+    const int nb = U + n, nv = nb + (with_tau ? 1 : 0);
+    const int mt = m + n + 1 + (with_tau ? 2 : 0);
+    const double *G = pb->cG + (size_t)c * m * U, *S = pb->cS + (size_t)c * m * n,
+                 *g = pb->cg + (size_t)c * m, *M = pb->cM + (size_t)c * Y * Y,
+                 *rho = pb->crho + (size_t)c * m;
+    double E[MAXNV * MAXNV]; /* n x n, column i = v_{i+1} - v_0 */
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) E[j * n + i] = R[(i + 1) * n + j] - R[j];
+    q->nv = nv; q->m = mt; q->cs = 1.0;
+    q->G = dalloc((size_t)mt * nv); q->h = dalloc(mt); q->rho = dalloc(mt);
+    for (int r = 0; r < m; ++r) {
+        double *row = q->G + (size_t)r * nv;
+        for (int j = 0; j < U; ++j) row[j] = G[r * U + j];
+        double hv = g[r];
+        for (int i = 0; i < n; ++i) {
+            double v = 0;
+            for (int j = 0; j < n; ++j) v += S[r * n + j] * E[j * n + i];
+            row[U + i] = -v;
+        }
+        for (int j = 0; j < n; ++j) hv += S[r * n + j] * R[j];
+        q->h[r] = hv;
+        q->rho[r] = rho[r];
+    }
+    for (int i = 0; i < n; ++i) { /* beta_i >= 0 */
+        q->G[(size_t)(m + i) * nv + U + i] = -1.0;
+        q->h[m + i] = 0.0; q->rho[m + i] = 1.0;
+    }
+    for (int i = 0; i < n; ++i) q->G[(size_t)(m + n) * nv + U + i] = 1.0; /* sum beta <= 1 */
+    q->h[m + n] = 1.0; q->rho[m + n] = 1.0;
+    if (with_tau) {
+        /* bar_V(beta) = Vr[0] + sum_i beta_i (Vr[i+1]-Vr[0])   (lib/oracle.py:88-90)
+         * bar_V - V >= eps_a        <=>  V + tau <= 0 with tau >= eps_a - bar_V
+         * bar_V - V >= eps_r V      <=>  V + tau <= 0 with tau >= -bar_V/(1+eps_r)
+         * (lib/oracle.py:94-95) */
+        double k2 = 1.0 / (1.0 + pb->eps_r);
+        double *r1 = q->G + (size_t)(m + n + 1) * nv, *r2 = q->G + (size_t)(m + n + 2) * nv;
+        double cs = 1.0; /* cost scale: tau = cs * tau', objective divided by cs */
+        for (int i = 0; i <= n; ++i) cs = fmax2(cs, fabs(Vr[i]));
+        q->cs = cs;
+        double n1 = cs, n2 = cs;
+        for (int i = 0; i < n; ++i) {
+            double dc = Vr[i + 1] - Vr[0];
+            r1[U + i] = -dc; r2[U + i] = -dc * k2;
+            n1 = fmax2(n1, fabs(dc)); n2 = fmax2(n2, fabs(dc * k2));
+        }
+        r1[nb] = -cs; r2[nb] = -cs;
+        q->h[m + n + 1] = Vr[0] - pb->eps_a; q->rho[m + n + 1] = n1;
+        q->h[m + n + 2] = Vr[0] * k2; q->rho[m + n + 2] = n2;
+    }
+    /* cost: y = [u; theta; 1] = Tm [u; beta; 1] */
+    double *Tm = dalloc((size_t)Y * Y), *MT = dalloc((size_t)Y * Y), *Mp = dalloc((size_t)Y * Y);
+    for (int i = 0; i < U; ++i) Tm[i * Y + i] = 1.0;
+    for (int j = 0; j < n; ++j) {
+        for (int i = 0; i < n; ++i) Tm[(U + j) * Y + U + i] = E[j * n + i];
+        Tm[(U + j) * Y + Y - 1] = R[j];
+    }
+    Tm[(Y - 1) * Y + Y - 1] = 1.0;
+    for (int i = 0; i < Y; ++i)
+        for (int j = 0; j < Y; ++j) {
+            double v = 0;
+            for (int k = 0; k < Y; ++k) v += M[i * Y + k] * Tm[k * Y + j];
+            MT[i * Y + j] = v;
+        }
+    for (int i = 0; i < Y; ++i)
+        for (int j = 0; j < Y; ++j) {
+            double v = 0;
+            for (int k = 0; k < Y; ++k) v += Tm[k * Y + i] * MT[k * Y + j];
+            Mp[i * Y + j] = v;
+        }
+    memset(q->H, 0, sizeof(q->H));
+    if (!with_tau) { /* scale the plain QP by its own Hessian/gradient magnitude */
+        double cs = 1.0;
+        for (int i = 0; i < nb; ++i) cs = fmax2(cs, fmax2(2.0 * fabs(Mp[i * Y + i]), 2.0 * fabs(Mp[i * Y + Y - 1])));
+        q->cs = cs;
+    }
+    for (int i = 0; i < nb; ++i) {
+        for (int j = 0; j < nb; ++j) q->H[i * nv + j] = 2.0 * Mp[i * Y + j] / q->cs;
+        q->f[i] = 2.0 * Mp[i * Y + Y - 1] / q->cs;
+    }
+    if (with_tau) q->f[nb] = 1.0;
+    q->cst = Mp[(Y - 1) * Y + Y - 1];
+    free(Tm); free(MT); free(Mp);
+}
+
+static void free_simplex_qp(simplex_qp *q) { free(q->G); free(q->h); free(q->rho); }
+
+/* Is candidate c alive on R?  (phase-1 over [u; beta]).  1 alive, 0 dead, <0 failure */
+static int alive_on_simplex(ehmo_problem *pb, int c, const double *R)
+{
+    simplex_qp q;
+    build_simplex_qp(pb, c, R, NULL, 0, &q);
+    double *Gn = dalloc((size_t)q.m * q.nv), *hn = dalloc(q.m);
+    int mo = prep_rows(q.nv, q.m, q.G, q.h, q.rho, Gn, hn);
+    int ret = (mo < 0) ? 0 : phase1(pb, q.nv, mo, Gn, hn, NULL);
+    free(Gn); free(hn); free_simplex_qp(&q);
+    return ret;
+}
+
+/* Solve the simplex QP of candidate c: with_tau=1 -> t*_c (eps-suboptimality epigraph
+ * problem), with_tau=0 -> min_{theta in R} V*_c(theta) (lib/oracle.py:75-79).
+ * returns 0 ok; zsol (nv) optional. */
+static int solve_simplex_qp(ehmo_problem *pb, int c, const double *R, const double *Vr,
+                            int with_tau, double *val, double *zsol)
+{
+    simplex_qp q;
+    build_simplex_qp(pb, c, R, Vr, with_tau, &q);
+    double *Gn = dalloc((size_t)q.m * q.nv), *hn = dalloc(q.m);
+    double z[MAXNV], obj = 0;
+    int mo = prep_rows(q.nv, q.m, q.G, q.h, q.rho, Gn, hn), st = 2;
+    if (mo >= 0) {
+        st = qp_solve(q.nv, mo, q.H, q.f, Gn, hn, NULL, z, &obj, NULL);
+        __sync_fetch_and_add(&pb->nsolves, 1);
+    }
+    if (st == 0) {
+        *val = q.cs * obj + q.cst;
+        if (zsol) {
+            memcpy(zsol, z, sizeof(double) * q.nv);
+            if (with_tau) zsol[q.nv - 1] *= q.cs;
+        }
+    } else if (getenv("EHMO_FAILTRACE")) {
+        fprintf(stderr, "SIMPLEXFAIL c %d tau %d R", c, with_tau);
+        for (int i = 0; i < (pb->n + 1) * pb->n; ++i) fprintf(stderr, " %.17g", R[i]);
+        fprintf(stderr, " Vr");
+        if (Vr) for (int i = 0; i <= pb->n; ++i) fprintf(stderr, " %.17g", Vr[i]);
+        fprintf(stderr, "\n");
+    }
+    free(Gn); free(hn); free_simplex_qp(&q);
+    return st;
+}
+
+/* One L-CSS node evaluation = bar_E_delta_R (lib/oracle.py:285-309) + bar_D_delta_R
+ * (:311-414) + in_variability_ball (:220-283), evaluated together because all three range
+ * over the same per-candidate epigraph problem
+ *
+ *     t*_c = min_{u,beta,tau}  V_c(u,theta(beta)) + tau
+ *            s.t. rows of c,  beta in simplex,  tau >= eps_a - bar_V(beta),
+ *                 tau >= -bar_V(beta)/(1+eps_r)
+ *
+ * so that  t*_c <= 0  <=>  candidate c satisfies the two bar_E inequalities (:94-95)
+ * somewhere in R.
+ *
+ * Canonical semantics:
+ *   converged  <=>  no alive candidate (delta_ref included) has t*_c <= 0        [bar_E]
+ *   delta*      =   argmin t*_c over {delta_ref} U {c alive, t*_c <= 0, P_theta_delta feasible
+ *                   and convergent at all n+1 vertices}; ties -> delta_ref first, then the
+ *                   smallest index.  If the argmin is delta_ref itself the result is "none",
+ *                   exactly the reference's rule for MOSEK returning delta_ref (:384-394).
+ *   theta*, V*  =   minimiser / V-part of delta*'s epigraph problem
+ *   var_small   =   max(Vr) - min_R V*_{delta_ref} < max(eps_a, eps_r V*)     (:282-283)
+ *
+ * lb[] (optional, one double per candidate, in/out) carries certified lower bounds of t*_c
+ * down a lineage: +inf = dead on R (phase-1 found no interior point; inherited by every
+ * descendant), finite = t*_c of an ancestor simplex (valid because bar_V of a child is
+ * <= bar_V of its parent on the child), -inf = unknown.  With prune!=0 a candidate whose
+ * bound already exceeds the incumbent is skipped -- this never changes the result. */
+int ehmo_lcss_eval(ehmo_problem *pb, const double *R, const double *Vr, int cref, double *lb,
+                   int prune, double *theta_star, double *Jv, double *Uv,
+                   ehmo_lcss_result *res)
+{
+    const int n = pb->n, nu = pb->nu, U = pb->U, nc = pb->ncand;
+    double *ts = dalloc(nc);
+    double tref = INFINITY, zref[MAXNV];
+    res->converged = 0; res->cstar = -1; res->var_small = 0; res->n_eval = 0; res->n_fail = 0;
+    /* delta_ref is feasible at every vertex by construction: no phase-1 */
+    if (cref >= 0) {
+        if (solve_simplex_qp(pb, cref, R, Vr, 1, &tref, zref) != 0) { tref = INFINITY; res->n_fail++; }
+        res->n_eval++;
+    }
+    res->t_ref = tref;
+    const double thr = tref <= 0.0 ? tref : 0.0; /* incumbent: only t*_c below this matter */
+    int any_improving = tref <= 0.0;
+    for (int c = 0; c < nc; ++c) {
+        ts[c] = NAN;
+        if (c == cref) continue;
+        if (lb && lb[c] == INFINITY) continue;                 /* dead */
+        if (lb && prune && lb[c] > thr) continue;              /* cannot be improving/argmin */
+        int al = alive_on_simplex(pb, c, R);
+        res->n_eval++;
+        if (al != 1) {
+            if (al < 0) res->n_fail++;
+            if (lb) lb[c] = INFINITY;
+            continue;
+        }
+        double t;
+        if (solve_simplex_qp(pb, c, R, Vr, 1, &t, NULL) != 0) {
+            res->n_fail++;
+            if (lb) lb[c] = INFINITY;
+            continue;
+        }
+        ts[c] = t;
+        if (lb) lb[c] = t;
+        if (t <= 0.0) any_improving = 1;
+    }
+    res->converged = !any_improving;
+    /* delta*: ascending t*, strictly better than delta_ref, eligible at all vertices */
+    int best = -1;
+    unsigned char *tried = (unsigned char *)calloc(nc, 1);
+    while (!res->converged) {
+        int c = -1;
+        for (int k = 0; k < nc; ++k)
+            if (k != cref && !tried[k] && ts[k] <= 0.0 && ts[k] < tref && (c < 0 || ts[k] < ts[c]))
+                c = k;
+        if (c < 0) break;
+        tried[c] = 1;
+        int ok = 1;
+        for (int i = 0; i <= n && ok; ++i)
+            ok = ehmo_p_theta_delta(pb, R + i * n, c, &Jv[i], Uv + i * nu) == 1;
+        if (ok) { best = c; break; }
+    }
+    free(tried);
+    if (best >= 0) {
+        double minV, t, z[MAXNV];
+        if (solve_simplex_qp(pb, cref, R, NULL, 0, &minV, NULL) != 0 ||
+            solve_simplex_qp(pb, best, R, Vr, 1, &t, z) != 0) {
+            best = -1;
+            res->n_fail++;
+        } else {
+            double Vstar = t - z[U + n], maxV = Vr[0];
+            for (int i = 1; i <= n; ++i) maxV = fmax2(maxV, Vr[i]);
+            for (int j = 0; j < n; ++j) {
+                double v = R[j];
+                for (int i = 0; i < n; ++i) v += (R[(i + 1) * n + j] - R[j]) * z[U + i];
+                theta_star[j] = v;
+            }
+            res->var_small = (maxV - minV) < fmax2(pb->eps_a, pb->eps_r * Vstar);
+        }
+    }
+    res->cstar = best;
+    free(ts);
+    return 0;
+}
+
+/* When a lineage changes its commutation (vertex costs Vr_old -> Vr_new on the same
+ * simplex) the inherited bounds stay valid after lowering them by
+ * d = max(0, max_i Vr_new[i]-Vr_old[i]):  bar_V_new <= bar_V_old + d on R. */
+void ehmo_lb_rebase(int n, int ncand, const double *Vr_old, const double *Vr_new, double *lb)
+{
+    double d = 0;
+    for (int i = 0; i <= n; ++i) d = fmax2(d, Vr_new[i] - Vr_old[i]);
+    if (d > 0) {
+        d += 1e-9 * (1.0 + d);
+        for (int c = 0; c < ncand; ++c)
+            if (isfinite(lb[c])) lb[c] -= d;
+    }
+}
+
+/* bar_E_delta_R as a stand-alone call (brute force over all candidates).  The reference
+ * signature has no delta_ref; every candidate goes through phase-1. */
+int ehmo_bar_e(ehmo_problem *pb, const double *R, const double *Vr, double *tstar)
+{
+    int subopt = 1;
+    for (int c = 0; c < pb->ncand; ++c) {
+        double t = NAN;
+        if (alive_on_simplex(pb, c, R) == 1 && solve_simplex_qp(pb, c, R, Vr, 1, &t, NULL) == 0) {
+            if (t <= 0.0) subopt = 0;
+        } else t = NAN;
+        if (tstar) tstar[c] = t;
+    }
+    return subopt;
+}
+
+/* bar_D_delta_R as a stand-alone call (brute force). */
+int ehmo_bar_d(ehmo_problem *pb, const double *R, const double *Vr, int cref,
+               double *theta_star, double *Jv, double *Uv, int *var_small)
+{
+    ehmo_lcss_result res;
+    ehmo_lcss_eval(pb, R, Vr, cref, NULL, 0, theta_star, Jv, Uv, &res);
+    *var_small = res.var_small;
+    return res.cstar;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* geometry (lib/tools.py:224-257, :134-150)                                              */
+/* ------------------------------------------------------------------------------------ */
+/* Longest edge = first maximum, in itertools.combinations order, of the Euclidean length;
+ * compared through the squared length accumulated left-to-right without FMA contraction so
+ * that CPU and GPU take bit-identical decisions (DESIGN.md "bit-exact geometry"). */
+void ehmo_split(int n, const double *R, double *S1, double *S2, int *ij)
+{
+    int bi = 0, bj = 1;
+    double best = -1.0;
+    for (int i = 0; i <= n; ++i)
+        for (int j = i + 1; j <= n; ++j) {
+            volatile double acc = 0.0;
+            for (int k = 0; k < n; ++k) {
+                volatile double d = R[i * n + k] - R[j * n + k];
+                volatile double d2 = d * d;
+                acc = acc + d2;
+            }
+            if (acc > best) { best = acc; bi = i; bj = j; }
+        }
+    memcpy(S1, R, sizeof(double) * (n + 1) * n);
+    memcpy(S2, R, sizeof(double) * (n + 1) * n);
+    for (int k = 0; k < n; ++k) {
+        double mid = (R[bi * n + k] + R[bj * n + k]) / 2.0;
+        S1[bi * n + k] = mid;
+        S2[bj * n + k] = mid;
+    }
+    ij[0] = bi; ij[1] = bj;
+}
+
+double ehmo_simplex_volume(int n, const double *R)
+{
+    double M[MAXNV * MAXNV], det = 1.0;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) M[j * n + i] = R[(i + 1) * n + j] - R[j];
+    for (int c = 0; c < n; ++c) { /* partial-pivot LU */
+        int pv = c;
+        for (int r = c + 1; r < n; ++r)
+            if (fabs(M[r * n + c]) > fabs(M[pv * n + c])) pv = r;
+        if (M[pv * n + c] == 0.0) return 0.0;
+        if (pv != c) {
+            for (int j = 0; j < n; ++j) { double t = M[c * n + j]; M[c * n + j] = M[pv * n + j]; M[pv * n + j] = t; }
+            det = -det;
+        }
+        det *= M[c * n + c];
+        for (int r = c + 1; r < n; ++r) {
+            double l = M[r * n + c] / M[c * n + c];
+            for (int j = c; j < n; ++j) M[r * n + j] -= l * M[c * n + j];
+        }
+    }
+    for (int k = 2; k <= n; ++k) det /= k;
+    return fabs(det);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* ECC / L-CSS recursion (lib/worker.py:241-417), serial depth-first per root             */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    ehmo_problem *pb;
+    ehmo_tree t;
+    long cap, max_nodes;
+    int prune;
+} builder;
+
+static long new_node(builder *b, const double *R, int root_id, int depth)
+{
+    ehmo_tree *t = &b->t;
+    const int n = t->n, nu = t->nu;
+    if (t->nnodes == b->cap) {
+        long nc = b->cap ? 2 * b->cap : 1024;
+        t->left = (int *)realloc(t->left, nc * sizeof(int));
+        t->right = (int *)realloc(t->right, nc * sizeof(int));
+        t->root_id = (int *)realloc(t->root_id, nc * sizeof(int));
+        t->depth = (int *)realloc(t->depth, nc * sizeof(int));
+        t->cand = (int *)realloc(t->cand, nc * sizeof(int));
+        t->closed = (unsigned char *)realloc(t->closed, nc);
+        t->vertices = (double *)realloc(t->vertices, nc * (n + 1) * n * sizeof(double));
+        t->vcost = (double *)realloc(t->vcost, nc * (n + 1) * sizeof(double));
+        t->vinput = (double *)realloc(t->vinput, nc * (n + 1) * nu * sizeof(double));
+        b->cap = nc;
+    }
+    long id = t->nnodes++;
+    t->left[id] = t->right[id] = -1;
+    t->root_id[id] = root_id; t->depth[id] = depth; t->cand[id] = -1; t->closed[id] = 0;
+    memcpy(t->vertices + id * (n + 1) * n, R, sizeof(double) * (n + 1) * n);
+    memset(t->vcost + id * (n + 1), 0, sizeof(double) * (n + 1));
+    memset(t->vinput + id * (n + 1) * nu, 0, sizeof(double) * (n + 1) * nu);
+    if (depth > t->max_depth) t->max_depth = depth;
+    return id;
+}
+
+static void lcss(builder *b, long id, double *lb);
+
+/* Worker.ecc (lib/worker.py:241-291) */
+static void ecc(builder *b, long id)
+{
+    ehmo_problem *pb = b->pb;
+    ehmo_tree *t = &b->t;
+    const int n = t->n, nu = t->nu;
+    if (t->error || t->nnodes >= b->max_nodes) return;
+    double R[MAXNV * MAXNV], Jv[MAXNV], Uv[MAXNV * MAXNV];
+    memcpy(R, t->vertices + id * (n + 1) * n, sizeof(double) * (n + 1) * n);
+    int c = ehmo_v_r(pb, R, Jv, Uv);
+    if (c < 0) {
+        /* worker.py:264-266: the barycentre must admit some commutation */
+        double cR[MAXNV], J;
+        for (int j = 0; j < n; ++j) {
+            cR[j] = 0;
+            for (int i = 0; i <= n; ++i) cR[j] += R[i * n + j];
+            cR[j] /= (n + 1);
+        }
+        int any = 0;
+        for (int k = 0; k < pb->ncand && !any; ++k)
+            any = ehmo_p_theta_delta(pb, cR, k, &J, NULL) == 1;
+        if (!any) { t->error = 1; return; }
+        double S1[MAXNV * MAXNV], S2[MAXNV * MAXNV];
+        int ij[2];
+        ehmo_split(n, R, S1, S2, ij);
+        long l = new_node(b, S1, t->root_id[id], t->depth[id] + 1);
+        long r = new_node(b, S2, t->root_id[id], t->depth[id] + 1);
+        t->left[id] = (int)l; t->right[id] = (int)r;
+        ecc(b, l);
+        ecc(b, r);
+    } else {
+        t->cand[id] = c;
+        memcpy(t->vcost + id * (n + 1), Jv, sizeof(double) * (n + 1));
+        memcpy(t->vinput + id * (n + 1) * nu, Uv, sizeof(double) * (n + 1) * nu);
+        double *lb = dalloc(pb->ncand);
+        for (int k = 0; k < pb->ncand; ++k) lb[k] = -INFINITY;
+        lcss(b, id, lb);
+        free(lb);
+    }
+}
+
+/* Worker.lcss (lib/worker.py:293-417).  lb: per-candidate bounds of this node (modified in
+ * place; children receive copies). */
+static void lcss(builder *b, long id, double *lb)
+{
+    ehmo_problem *pb = b->pb;
+    ehmo_tree *t = &b->t;
+    const int n = t->n, nu = t->nu, nc = pb->ncand;
+    double R[MAXNV * MAXNV], Vr[MAXNV], Ur[MAXNV * MAXNV];
+    for (;;) {
+        if (t->error || t->nnodes >= b->max_nodes) break;
+        memcpy(R, t->vertices + id * (n + 1) * n, sizeof(double) * (n + 1) * n);
+        memcpy(Vr, t->vcost + id * (n + 1), sizeof(double) * (n + 1));
+        memcpy(Ur, t->vinput + id * (n + 1) * nu, sizeof(double) * (n + 1) * nu);
+        int cref = t->cand[id];
+        double th[MAXNV], Jn[MAXNV], Un[MAXNV * MAXNV];
+        ehmo_lcss_result res;
+        ehmo_lcss_eval(pb, R, Vr, cref, lb, b->prune, th, Jn, Un, &res);
+        t->nfail += res.n_fail;
+        if (getenv("EHMO_TRACE"))
+            fprintf(stderr, "node %ld depth %d cref %d evaluated %d tref %.4g conv %d cstar %d vs %d\n",
+                    id, t->depth[id], cref, res.n_eval, res.t_ref, res.converged, res.cstar, res.var_small);
+        if (res.converged) { /* worker.py:368-375 close leaf */
+            t->closed[id] = 1;
+            t->nleaves++;
+            break;
+        }
+        int cnew = cref;
+        if (res.cstar >= 0) { /* worker.py:389-395 */
+            cnew = res.cstar;
+            ehmo_lb_rebase(n, nc, Vr, Jn, lb);
+            lb[cref] = -INFINITY; /* the old commutation becomes an ordinary candidate */
+            memcpy(Vr, Jn, sizeof(double) * (n + 1));
+            memcpy(Ur, Un, sizeof(double) * (n + 1) * nu);
+        }
+        if (res.cstar >= 0 && res.var_small) { /* worker.py:396-401: swap, same node */
+            t->cand[id] = cnew;
+            memcpy(t->vcost + id * (n + 1), Vr, sizeof(double) * (n + 1));
+            memcpy(t->vinput + id * (n + 1) * nu, Ur, sizeof(double) * (n + 1) * nu);
+            continue;
+        }
+        /* worker.py:403-417: split, re-solve only the midpoint vertex */
+        double S1[MAXNV * MAXNV], S2[MAXNV * MAXNV], Jm, Um[MAXNV];
+        int ij[2];
+        ehmo_split(n, R, S1, S2, ij);
+        if (ehmo_p_theta_delta(pb, S1 + ij[0] * n, cnew, &Jm, Um) != 1) {
+            t->error = 2; /* cannot happen for a convex feasible set; reference would raise */
+            break;
+        }
+        long l = new_node(b, S1, t->root_id[id], t->depth[id] + 1);
+        long r = new_node(b, S2, t->root_id[id], t->depth[id] + 1);
+        t->left[id] = (int)l; t->right[id] = (int)r;
+        for (int side = 0; side < 2; ++side) {
+            long ch = side ? r : l;
+            t->cand[ch] = cnew;
+            memcpy(t->vcost + ch * (n + 1), Vr, sizeof(double) * (n + 1));
+            memcpy(t->vinput + ch * (n + 1) * nu, Ur, sizeof(double) * (n + 1) * nu);
+            t->vcost[ch * (n + 1) + ij[side]] = Jm;
+            memcpy(t->vinput + (ch * (n + 1) + ij[side]) * nu, Um, sizeof(double) * nu);
+        }
+        double *ll = dcopy(lb, nc);
+        lcss(b, l, ll);
+        free(ll);
+        lcss(b, r, lb);
+        break;
+    }
+}
+
+typedef struct {
+    ehmo_problem *pb;
+    int nroots;
+    const double *roots;
+    int *next;
+    long max_nodes;
+    builder b;
+    int *root_of; /* unused */
+} thread_arg;
+
+static void *thread_main(void *p)
+{
+    thread_arg *a = (thread_arg *)p;
+    const int n = a->pb->n;
+    for (;;) {
+        int r = __sync_fetch_and_add(a->next, 1);
+        if (r >= a->nroots) break;
+        long id = new_node(&a->b, a->roots + (size_t)r * (n + 1) * n, r, 0);
+        ecc(&a->b, id);
+    }
+    return NULL;
+}
+
+ehmo_tree *ehmo_partition(ehmo_problem *pb, int nroots, const double *roots, int nthreads,
+                          long max_nodes, int prune)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > nroots) nthreads = nroots;
+    if (max_nodes <= 0) max_nodes = 1L << 40;
+    int next = 0;
+    long solves0 = pb->nsolves;
+    thread_arg *args = (thread_arg *)calloc(nthreads, sizeof(thread_arg));
+    pthread_t *th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
+    for (int i = 0; i < nthreads; ++i) {
+        args[i].pb = pb; args[i].nroots = nroots; args[i].roots = roots; args[i].next = &next;
+        args[i].b.pb = pb; args[i].b.max_nodes = max_nodes; args[i].b.prune = prune;
+        args[i].b.t.n = pb->n; args[i].b.t.nu = pb->nu;
+        pthread_create(&th[i], NULL, thread_main, &args[i]);
+    }
+    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
+    /* merge per-thread trees */
+    ehmo_tree *t = (ehmo_tree *)calloc(1, sizeof(ehmo_tree));
+    const int n = pb->n, nu = pb->nu;
+    t->n = n; t->nu = nu;
+    long total = 0;
+    for (int i = 0; i < nthreads; ++i) total += args[i].b.t.nnodes;
+    t->left = (int *)malloc(total * sizeof(int)); t->right = (int *)malloc(total * sizeof(int));
+    t->root_id = (int *)malloc(total * sizeof(int)); t->depth = (int *)malloc(total * sizeof(int));
+    t->cand = (int *)malloc(total * sizeof(int)); t->closed = (unsigned char *)malloc(total ? total : 1);
+    t->vertices = dalloc(total * (n + 1) * n); t->vcost = dalloc(total * (n + 1));
+    t->vinput = dalloc(total * (n + 1) * nu);
+    long off = 0;
+    for (int i = 0; i < nthreads; ++i) {
+        ehmo_tree *s = &args[i].b.t;
+        for (long k = 0; k < s->nnodes; ++k) {
+            t->left[off + k] = s->left[k] < 0 ? -1 : (int)(s->left[k] + off);
+            t->right[off + k] = s->right[k] < 0 ? -1 : (int)(s->right[k] + off);
+            t->root_id[off + k] = s->root_id[k]; t->depth[off + k] = s->depth[k];
+            t->cand[off + k] = s->cand[k]; t->closed[off + k] = s->closed[k];
+        }
+        if (s->nnodes) {
+            memcpy(t->vertices + off * (n + 1) * n, s->vertices, s->nnodes * (n + 1) * n * sizeof(double));
+            memcpy(t->vcost + off * (n + 1), s->vcost, s->nnodes * (n + 1) * sizeof(double));
+            memcpy(t->vinput + off * (n + 1) * nu, s->vinput, s->nnodes * (n + 1) * nu * sizeof(double));
+        }
+        off += s->nnodes;
+        t->nleaves += s->nleaves;
+        if (s->max_depth > t->max_depth) t->max_depth = s->max_depth;
+        if (s->error) t->error = s->error;
+        t->nfail += s->nfail;
+        free(s->left); free(s->right); free(s->root_id); free(s->depth); free(s->cand);
+        free(s->closed); free(s->vertices); free(s->vcost); free(s->vinput);
+    }
+    t->nnodes = total;
+    t->nsolves = pb->nsolves - solves0;
+    free(args); free(th);
+    return t;
+}
+
+void ehmo_tree_free(ehmo_tree *t)
+{
+    if (!t) return;
+    free(t->left); free(t->right); free(t->root_id); free(t->depth); free(t->cand);
+    free(t->closed); free(t->vertices); free(t->vcost); free(t->vinput);
+    free(t);
+}
