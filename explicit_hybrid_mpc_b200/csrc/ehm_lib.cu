@@ -1,0 +1,395 @@
+// ehm_lib.cu -- problem object, candidate condensation and the batched oracle entry points
+// of libehm_b200.so (C-ABI in include/ehm.h).  sm_100a only; no CPU fallback: every entry
+// point fails with EHM_ECUDA when no CUDA device is usable.
+#include <cstdio>
+#include <cstring>
+
+#include "ehm_common.cuh"
+
+namespace ehm {
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+}  // namespace ehm
+
+using namespace ehm;
+
+// ---------------------------------------------------------------------------------------
+// compiled problem shapes <U, NX, MR>: U = N*n_u inputs, NX = n, MR = ceil(rows/32) where
+// rows = N*p + n + 3 (stage rows + simplex rows + two epigraph rows)
+// ---------------------------------------------------------------------------------------
+#define EHM_FOR_EACH_CFG(X) X(0, 5, 4, 7) /* inverted pendulum, N=5 */
+
+static int find_cfg(int U, int NX, int rows_total)
+{
+    const int MR = (rows_total + 31) / 32;
+#define X(ID, UU, NN, MM) \
+    if (U == UU && NX == NN && MR == MM) return ID;
+    EHM_FOR_EACH_CFG(X)
+#undef X
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+constexpr int kWarpsPerCta = 4;
+
+__device__ __forceinline__ long long next_item(DevCounters *cnt, int lane)
+{
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(&cnt->work, 1ull);
+    return (long long)__shfl_sync(kFull, v, 0);
+}
+
+__device__ __forceinline__ void account(DevCounters *cnt, const SolveOut &o, int lane)
+{
+    if (lane == 0) {
+        atomicAdd(&cnt->iters, (unsigned long long)o.iters);
+        atomicAdd(&cnt->solves, (unsigned long long)o.nsolves);
+        if (o.status < 0) atomicAdd(&cnt->fails, 1ull);
+    }
+}
+
+template <int U, int NX, int MR>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+k_point_batch(DevTables tb, int B, const double *__restrict__ theta, const int *__restrict__ cand,
+              double *J, double *u0, int *status, DevCounters *cnt)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, MR>::kDoubles;
+    for (;;) {
+        const long long b = next_item(cnt, lane);
+        if (b >= B) break;
+        const int c = cand[b];
+        SolveOut o{0, 0.0, 0, 0};
+        if (c >= 0 && c < tb.ncand)
+            o = solve_point<U, NX, MR>(tb, c, theta + (size_t)b * NX, ws, u0 ? u0 + (size_t)b * tb.nu : nullptr, lane);
+        account(cnt, o, lane);
+        if (lane == 0) {
+            status[b] = o.status;
+            J[b] = o.val;
+        }
+        __syncwarp();
+    }
+}
+
+template <int U, int NX, int MR>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+k_simplex_batch(DevTables tb, int B, const double *__restrict__ R, const double *__restrict__ Vr,
+                const int *__restrict__ cand, int mode, int with_phase1, double *val, double *sol,
+                int *status, DevCounters *cnt)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, MR>::kDoubles;
+    for (;;) {
+        const long long b = next_item(cnt, lane);
+        if (b >= B) break;
+        const int c = cand[b];
+        SolveOut o{0, 0.0, 0, 0};
+        if (c >= 0 && c < tb.ncand)
+            o = solve_simplex<U, NX, MR>(tb, c, R + (size_t)b * (NX + 1) * NX,
+                                         Vr ? Vr + (size_t)b * (NX + 1) : nullptr, mode,
+                                         with_phase1 != 0, ws,
+                                         sol ? sol + (size_t)b * (NX + 1) : nullptr, lane);
+        account(cnt, o, lane);
+        if (lane == 0) {
+            status[b] = o.status;
+            val[b] = o.val;
+        }
+        __syncwarp();
+    }
+}
+
+// Longest-edge bisection, one thread per simplex (lib/tools.py:224-257).  The squared edge
+// length is accumulated left to right with explicit round-to-nearest mul/add (no FMA) so
+// that the first-maximum decision is bit-identical to the CPU restatement.
+__global__ void k_split_batch(int n, int B, const double *__restrict__ R, double *S1, double *S2,
+                              int *ij)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double *Rb = R + (size_t)b * (n + 1) * n;
+    int bi = 0, bj = 1;
+    double best = -1.0;
+    for (int i = 0; i <= n; ++i)
+        for (int j = i + 1; j <= n; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) {
+                const double d = __dsub_rn(Rb[i * n + k], Rb[j * n + k]);
+                acc = __dadd_rn(acc, __dmul_rn(d, d));
+            }
+            if (acc > best) {
+                best = acc;
+                bi = i;
+                bj = j;
+            }
+        }
+    double *A = S1 + (size_t)b * (n + 1) * n, *Bq = S2 + (size_t)b * (n + 1) * n;
+    for (int e = 0; e < (n + 1) * n; ++e) {
+        A[e] = Rb[e];
+        Bq[e] = Rb[e];
+    }
+    for (int k = 0; k < n; ++k) {
+        const double mid = __ddiv_rn(__dadd_rn(Rb[bi * n + k], Rb[bj * n + k]), 2.0);
+        A[bi * n + k] = mid;
+        Bq[bj * n + k] = mid;
+    }
+    ij[2 * b] = bi;
+    ij[2 * b + 1] = bj;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: condensation of every commutation candidate (mode sequence)
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// x_k = T [u; theta; 1] with T an n x Y matrix; rows/cost follow from the stage data.
+struct Condenser {
+    const ehm_problem_desc &d;
+    int n, nu, N, K, p, U, m, MP, Y;
+    explicit Condenser(const ehm_problem_desc &desc) : d(desc)
+    {
+        n = d.n; nu = d.nu; N = d.N; K = d.K; p = d.p;
+        U = N * nu; m = N * p; MP = ((m + n + 3 + 31) / 32) * 32; Y = U + n + 1;
+    }
+    void run(int c, double *G, double *S, double *g, double *rho, double *M) const
+    {
+        std::vector<int> seq(N);
+        for (int k = N - 1; k >= 0; --k) { seq[k] = c % K; c /= K; }
+        std::vector<double> T((size_t)n * Y, 0.0), Tn((size_t)n * Y), WT((size_t)n * Y);
+        for (int i = 0; i < n; ++i) T[(size_t)i * Y + U + i] = 1.0;
+        std::fill(M, M + (size_t)Y * Y, 0.0);
+        for (int col = 0; col < U; ++col) std::fill(G + (size_t)col * MP, G + (size_t)(col + 1) * MP, 0.0);
+        for (int col = 0; col < n; ++col) std::fill(S + (size_t)col * MP, S + (size_t)(col + 1) * MP, 0.0);
+        std::fill(g, g + MP, 1.0);
+        std::fill(rho, rho + MP, 0.0);
+        for (int k = 0; k < N; ++k) {
+            const int i = seq[k];
+            const double *Ci = d.C + (size_t)i * p * n, *Di = d.D + (size_t)i * p * nu,
+                         *ei = d.e + (size_t)i * p, *Ai = d.A + (size_t)i * n * n,
+                         *Bi = d.B + (size_t)i * n * nu, *wi = d.w + (size_t)i * n;
+            for (int r = 0; r < p; ++r) {
+                const int row = k * p + r;
+                double nat = 0.0;
+                for (int col = 0; col < U; ++col) {
+                    double v = 0.0;
+                    for (int a = 0; a < n; ++a) v += Ci[r * n + a] * T[(size_t)a * Y + col];
+                    if (col / nu == k) v += Di[r * nu + col % nu];
+                    G[(size_t)col * MP + row] = v;
+                    nat = std::max(nat, std::fabs(v));
+                }
+                for (int col = 0; col < n; ++col) {
+                    double v = 0.0;
+                    for (int a = 0; a < n; ++a) v += Ci[r * n + a] * T[(size_t)a * Y + U + col];
+                    S[(size_t)col * MP + row] = -v;
+                    nat = std::max(nat, std::fabs(v) * d.theta_scale[col]);
+                }
+                double gc = ei[r];
+                for (int a = 0; a < n; ++a) gc -= Ci[r * n + a] * T[(size_t)a * Y + Y - 1];
+                g[row] = gc;
+                rho[row] = nat;
+            }
+            for (int a = 0; a < nu; ++a) {
+                for (int b = 0; b < nu; ++b) M[(size_t)(k * nu + a) * Y + k * nu + b] += d.R[a * nu + b];
+                M[(size_t)(k * nu + a) * Y + Y - 1] += 0.5 * d.ru[i * nu + a];
+                M[(size_t)(Y - 1) * Y + k * nu + a] += 0.5 * d.ru[i * nu + a];
+            }
+            for (int a = 0; a < n; ++a)
+                for (int col = 0; col < Y; ++col) {
+                    double v = 0.0;
+                    for (int b = 0; b < n; ++b) v += Ai[a * n + b] * T[(size_t)b * Y + col];
+                    if (col < U && col / nu == k) v += Bi[a * nu + col % nu];
+                    if (col == Y - 1) v += wi[a];
+                    Tn[(size_t)a * Y + col] = v;
+                }
+            T.swap(Tn);
+            const double *W = (k + 1 < N) ? d.Q : d.P;  // mpc_library.py:515-517
+            for (int a = 0; a < n; ++a)
+                for (int col = 0; col < Y; ++col) {
+                    double v = 0.0;
+                    for (int b = 0; b < n; ++b) v += W[a * n + b] * T[(size_t)b * Y + col];
+                    WT[(size_t)a * Y + col] = v;
+                }
+            for (int r2 = 0; r2 < Y; ++r2)
+                for (int col = 0; col < Y; ++col) {
+                    double v = 0.0;
+                    for (int a = 0; a < n; ++a) v += T[(size_t)a * Y + r2] * WT[(size_t)a * Y + col];
+                    M[(size_t)r2 * Y + col] += v;
+                }
+        }
+    }
+};
+
+template <typename KernelT>
+int set_smem(KernelT kernel, size_t bytes)
+{
+    EHM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return EHM_OK;
+}
+
+}  // namespace
+
+extern "C" const char *ehm_last_error(void) { return g_last_error.c_str(); }
+extern "C" int64_t ehm_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" int ehm_problem_create(const ehm_problem_desc *desc, ehm_problem **out)
+{
+    if (!desc || !out) return fail(EHM_EINVAL, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(EHM_ECUDA, "no CUDA device: libehm_b200 has no CPU path");
+    Condenser cd(*desc);
+    const int cfg = find_cfg(cd.U, cd.n, cd.m + cd.n + 3);
+    if (cfg < 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "problem shape U=%d n=%d rows=%d has no compiled kernel", cd.U,
+                 cd.n, cd.m + cd.n + 3);
+        return fail(EHM_EINVAL, buf);
+    }
+    double nc = 1;
+    for (int k = 0; k < cd.N; ++k) nc *= cd.K;
+    if (nc > 2e6) return fail(EHM_EINVAL, "too many commutation candidates");
+    const int ncand = (int)nc;
+    ehm_problem *pb = new ehm_problem();
+    pb->cfg = cfg;
+    DevTables &tb = pb->tb;
+    tb.n = cd.n; tb.nu = cd.nu; tb.N = cd.N; tb.K = cd.K; tb.p = cd.p;
+    tb.U = cd.U; tb.m = cd.m; tb.MP = cd.MP; tb.Y = cd.Y; tb.ncand = ncand;
+    tb.eps_a = desc->eps_a; tb.eps_r = desc->eps_r;
+    const size_t szG = (size_t)ncand * cd.U * cd.MP, szS = (size_t)ncand * cd.n * cd.MP,
+                 szg = (size_t)ncand * cd.MP, szM = (size_t)ncand * cd.Y * cd.Y;
+    std::vector<double> hG(szG), hS(szS), hg(szg), hr(szg), hM(szM);
+    for (int c = 0; c < ncand; ++c)
+        cd.run(c, hG.data() + (size_t)c * cd.U * cd.MP, hS.data() + (size_t)c * cd.n * cd.MP,
+               hg.data() + (size_t)c * cd.MP, hr.data() + (size_t)c * cd.MP,
+               hM.data() + (size_t)c * cd.Y * cd.Y);
+    cudaError_t e = cudaSuccess;
+    auto up = [&](double **dst, const std::vector<double> &src) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc((void **)dst, src.size() * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(double), cudaMemcpyHostToDevice);
+    };
+    up(&pb->dG, hG); up(&pb->dS, hS); up(&pb->dg, hg); up(&pb->drho, hr); up(&pb->dM, hM);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&pb->dcnt, sizeof(DevCounters));
+    if (e == cudaSuccess) e = cudaMemset(pb->dcnt, 0, sizeof(DevCounters));
+    if (e != cudaSuccess) {
+        ehm_problem_destroy(pb);
+        return fail(EHM_ECUDA, std::string("problem upload: ") + cudaGetErrorString(e));
+    }
+    tb.G = pb->dG; tb.S = pb->dS; tb.g = pb->dg; tb.rho = pb->drho; tb.M = pb->dM;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&pb->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    *out = pb;
+    return EHM_OK;
+}
+
+extern "C" int ehm_problem_destroy(ehm_problem *p)
+{
+    if (!p) return EHM_OK;
+    cudaFree(p->dG); cudaFree(p->dS); cudaFree(p->dg); cudaFree(p->drho); cudaFree(p->dM);
+    cudaFree(p->dcnt);
+    delete p;
+    return EHM_OK;
+}
+
+extern "C" int ehm_set_eps(ehm_problem *p, double eps_a, double eps_r)
+{
+    if (!p) return fail(EHM_EINVAL, "null problem");
+    p->tb.eps_a = eps_a;
+    p->tb.eps_r = eps_r;
+    return EHM_OK;
+}
+
+extern "C" int ehm_num_candidates(const ehm_problem *p) { return p ? p->tb.ncand : 0; }
+
+static int grid_for(const ehm_problem *p, long long items)
+{
+    const long long ctas = (items + kWarpsPerCta - 1) / kWarpsPerCta;
+    const long long cap = (long long)p->sm_count * 2;  // 2 CTAs (8 warps) resident per SM
+    return (int)std::max(1ll, std::min(ctas, cap));
+}
+
+extern "C" int ehm_qp_theta_delta_batch(ehm_problem *p, int B, const double *d_theta,
+                                        const int *d_cand, double *d_J, double *d_u0,
+                                        int *d_status, void *stream)
+{
+    if (!p || B < 0 || !d_theta || !d_cand || !d_J || !d_status) return fail(EHM_EINVAL, "bad argument");
+    if (B == 0) return EHM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    EHM_CUDA(cudaMemsetAsync(&p->dcnt->work, 0, sizeof(unsigned long long), st));
+    switch (p->cfg) {
+#define X(ID, UU, NN, MM)                                                                     \
+    case ID: {                                                                                \
+        auto kern = k_point_batch<UU, NN, MM>;                                                \
+        const size_t sm = (size_t)kWarpsPerCta * WarpWs<UU, NN, MM>::kDoubles * sizeof(double); \
+        int rc = set_smem(kern, sm);                                                          \
+        if (rc) return rc;                                                                    \
+        kern<<<grid_for(p, B), 32 * kWarpsPerCta, sm, st>>>(p->tb, B, d_theta, d_cand, d_J, d_u0, \
+                                                            d_status, p->dcnt);               \
+        break;                                                                                \
+    }
+        EHM_FOR_EACH_CFG(X)
+#undef X
+    default: return fail(EHM_EINVAL, "no kernel for this problem shape");
+    }
+    g_launches++;
+    EHM_CUDA(cudaGetLastError());
+    return EHM_OK;
+}
+
+extern "C" int ehm_simplex_batch(ehm_problem *p, int B, const double *d_R, const double *d_Vr,
+                                 const int *d_cand, int mode, int with_phase1, double *d_val,
+                                 double *d_sol, int *d_status, void *stream)
+{
+    if (!p || B < 0 || !d_R || !d_cand || !d_val || !d_status) return fail(EHM_EINVAL, "bad argument");
+    if (mode < 0 || mode > 2 || (mode == EHM_SX_TQP && !d_Vr)) return fail(EHM_EINVAL, "bad mode");
+    if (B == 0) return EHM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    EHM_CUDA(cudaMemsetAsync(&p->dcnt->work, 0, sizeof(unsigned long long), st));
+    switch (p->cfg) {
+#define X(ID, UU, NN, MM)                                                                     \
+    case ID: {                                                                                \
+        auto kern = k_simplex_batch<UU, NN, MM>;                                              \
+        const size_t sm = (size_t)kWarpsPerCta * WarpWs<UU, NN, MM>::kDoubles * sizeof(double); \
+        int rc = set_smem(kern, sm);                                                          \
+        if (rc) return rc;                                                                    \
+        kern<<<grid_for(p, B), 32 * kWarpsPerCta, sm, st>>>(p->tb, B, d_R, d_Vr, d_cand, mode, \
+                                                            with_phase1, d_val, d_sol,        \
+                                                            d_status, p->dcnt);               \
+        break;                                                                                \
+    }
+        EHM_FOR_EACH_CFG(X)
+#undef X
+    default: return fail(EHM_EINVAL, "no kernel for this problem shape");
+    }
+    g_launches++;
+    EHM_CUDA(cudaGetLastError());
+    return EHM_OK;
+}
+
+extern "C" int ehm_split_batch(int n, int B, const double *d_R, double *d_S1, double *d_S2,
+                               int *d_ij, void *stream)
+{
+    if (n < 1 || B < 0 || !d_R || !d_S1 || !d_S2 || !d_ij) return fail(EHM_EINVAL, "bad argument");
+    if (B == 0) return EHM_OK;
+    k_split_batch<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, B, d_R, d_S1, d_S2, d_ij);
+    g_launches++;
+    EHM_CUDA(cudaGetLastError());
+    return EHM_OK;
+}
+
+// counters (host view) -- used by the Python layer and bench.py
+extern "C" int ehm_read_counters(ehm_problem *p, int64_t *iters, int64_t *solves, int64_t *fails)
+{
+    if (!p) return fail(EHM_EINVAL, "null problem");
+    DevCounters h;
+    EHM_CUDA(cudaMemcpy(&h, p->dcnt, sizeof h, cudaMemcpyDeviceToHost));
+    if (iters) *iters = (int64_t)h.iters;
+    if (solves) *solves = (int64_t)h.solves;
+    if (fails) *fails = (int64_t)h.fails;
+    return EHM_OK;
+}

@@ -161,6 +161,7 @@ class InvertedPendulumOnCart:
         self.ang_err, self.rate_err = np.deg2rad(5), np.deg2rad(20)
         self.D_x = np.diag([self.p_err, self.ang_err, self.v_err, self.rate_err])
         self.D_u = np.diag([F_max])
+        self.theta_scale = np.diag(self.D_x).copy()   # natural magnitude of theta
         Qhat = np.diag([0.1, 1, 1, 10])
         Rhat = np.eye(1)
         Dxi, Dui = np.linalg.inv(self.D_x), np.linalg.inv(self.D_u)
@@ -237,6 +238,7 @@ class SyntheticMPLP:
     def __init__(self, n=8, nz=16, rows=48, K=4, seed=20260922):
         rng = np.random.default_rng(seed)
         self.n_x, self.n_u, self.N, self.delta_size = n, nz, 1, K
+        self.theta_scale = np.ones(n)
         A = rng.standard_normal((K, rows, nz))
         c = rng.standard_normal((K, nz))
         S = rng.standard_normal((K, rows, n))

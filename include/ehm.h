@@ -1,0 +1,129 @@
+/*
+ * ehm.h -- C-ABI of the B200 explicit-hybrid-MPC partitioning engine (libehm_b200.so).
+ *
+ * Drop-in boundary for the hot path of dmalyuta/explicit_hybrid_mpc: the per-simplex
+ * optimisation oracle (lib/oracle.py), the ECC/L-CSS recursion and task farm
+ * (lib/worker.py, lib/scheduler.py), the longest-edge split (lib/tools.py:224-257) and the
+ * tree node storage (lib/tree.py).  The reference has no FFI of its own (100% Python over
+ * CVXPY->MOSEK and mpi4py); each entry point below names the reference interface it
+ * replaces.  Plain C types only: no torch, no C++ in the signatures.  All functions return
+ * 0 on success and a negative EHM_E* code on failure; nothing throws.
+ *
+ * Pointers named d_* are DEVICE pointers (e.g. torch.Tensor.data_ptr() of a CUDA tensor),
+ * everything else is a HOST pointer.  `stream` is a cudaStream_t passed as void* (NULL =
+ * default stream).  The library never allocates output buffers for the batch calls; the
+ * caller owns them.
+ */
+#ifndef EHM_H
+#define EHM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EHM_OK            0
+#define EHM_EINVAL       -1   /* bad argument / unsupported problem size                     */
+#define EHM_ECUDA        -2   /* CUDA runtime error (ehm_last_error() has the text)           */
+#define EHM_ENOMEM       -3
+#define EHM_EINFEASIBLE  -4   /* "STOP, Theta contains infeasible regions" (worker.py:265-266) */
+#define EHM_ECAPACITY    -5   /* node store / frontier capacity exhausted                     */
+#define EHM_ENUMERIC     -6   /* midpoint vertex problem failed (worker.py would raise)       */
+
+/* Canonical tolerances; identical, by specification, to oracle/ehm_oracle.h */
+#define EHM_TOL_IPM   1e-9
+#define EHM_TOL_DUAL  1e-2
+#define EHM_TAU_INT   1e-7
+#define EHM_TAU_CONST 1e-7
+#define EHM_ZERO_ROW  1e-13
+#define EHM_MAX_ITER  80
+
+typedef struct ehm_problem ehm_problem;
+
+/* Switched-affine MPC description (host arrays, row-major fp64); see
+ * explicit_hybrid_mpc_b200/mpc_library.py:HybridMPCProblem.  Replaces the CVXPY problem
+ * templates built by Oracle.__init__ (lib/oracle.py:23-102) from the MPC object
+ * (lib/mpc_library.py:474-554). */
+typedef struct {
+    int n, nu, N, K, p;
+    const double *A, *B, *w;        /* (K,n,n) (K,n,nu) (K,n)              */
+    const double *C, *D, *e;        /* (K,p,n) (K,p,nu) (K,p)              */
+    const double *Q, *P, *R, *ru;   /* (n,n) (n,n) (nu,nu) (K,nu)          */
+    const double *theta_scale;      /* (n,) natural magnitude of theta     */
+    double eps_a, eps_r;            /* Oracle(mpc,eps_a,eps_r)             */
+} ehm_problem_desc;
+
+int ehm_problem_create(const ehm_problem_desc *desc, ehm_problem **out);
+int ehm_problem_destroy(ehm_problem *p);
+int ehm_set_eps(ehm_problem *p, double eps_a, double eps_r);
+int ehm_num_candidates(const ehm_problem *p);     /* K^N one-hot commutations */
+const char *ehm_last_error(void);
+/* number of hand-written kernels launched by this library since load (bench gpu_launches) */
+int64_t ehm_kernel_launches(void);
+
+/* ---- batched oracle sub-problems (one warp per problem) ------------------------------ */
+/* P_theta_delta for B (theta, candidate) pairs  [lib/oracle.py:141-173].
+ * d_status[b]: 1 feasible & converged (d_J, d_u0 valid), 0 infeasible, -1 numerical failure.
+ * d_u0 is the scaled first input uhat_0 (multiply by u_scale on the host). */
+int ehm_qp_theta_delta_batch(ehm_problem *p, int B, const double *d_theta, const int *d_cand,
+                             double *d_J, double *d_u0, int *d_status, void *stream);
+
+/* Simplex problems over R (B,(n+1),n) for B (simplex, candidate) pairs.
+ *  mode EHM_SX_ALIVE : phase-1 only                  -> d_val = sigma*
+ *  mode EHM_SX_TQP   : eps-suboptimality epigraph QP -> d_val = t*_c, d_sol = [beta(n), V*]
+ *                      (constraints lib/oracle.py:88-97; needs d_Vr (B,n+1))
+ *  mode EHM_SX_MINV  : min_{theta in R} V*_c(theta)  -> d_val, d_sol = [beta(n), V*]
+ *                      (lib/oracle.py:75-79)
+ * with_phase1 != 0 runs the alive test first for TQP/MINV.
+ * d_status[b]: 1 ok, 0 not alive / infeasible, -1 numerical failure. */
+#define EHM_SX_ALIVE 0
+#define EHM_SX_TQP   1
+#define EHM_SX_MINV  2
+int ehm_simplex_batch(ehm_problem *p, int B, const double *d_R, const double *d_Vr,
+                      const int *d_cand, int mode, int with_phase1, double *d_val,
+                      double *d_sol, int *d_status, void *stream);
+
+/* Longest-edge bisection of B simplices  [lib/tools.py:224-257].  d_ij (B,2) int32. */
+int ehm_split_batch(int n, int B, const double *d_R, double *d_S1, double *d_S2, int *d_ij,
+                    void *stream);
+
+/* ---- the fused partition loop -------------------------------------------------------- */
+/* Replaces scheduler.main()/Worker.spin()/Worker.ecc()/Worker.lcss() and build_tree()
+ * (lib/scheduler.py:364-691, lib/worker.py:164-461): a device-resident LIFO frontier of
+ * open simplices is popped `wave` nodes at a time; every node is run through the oracle
+ * kernels, closed or split, and its children are pushed back.  Results land in a flat node
+ * store (the device analogue of lib/tree.py) which is copied to the caller's HOST buffers. */
+typedef struct {
+    int wave;              /* nodes popped per wave (0 = default)                          */
+    int64_t max_nodes;     /* node-store capacity (0 = default)                            */
+    int64_t max_frontier;  /* frontier capacity in entries (0 = default)                   */
+    int64_t node_budget;   /* stop (cleanly) once this many nodes exist; 0 = run to the end */
+    int verbose;
+} ehm_partition_opts;
+
+typedef struct {
+    int64_t nnodes, nleaves, nsolves, niters, nfail, nwaves, nlaunches;
+    int64_t open_left;     /* frontier entries left when a node_budget stopped the run      */
+    int max_depth;
+    double device_ms;      /* CUDA-event time of the whole loop                            */
+} ehm_partition_stats;
+
+typedef struct ehm_partition ehm_partition;
+
+/* roots: host (nroots,(n+1),n).  Runs until the frontier is empty (or node_budget). */
+int ehm_partition_run(ehm_problem *p, int nroots, const double *roots,
+                      const ehm_partition_opts *opts, ehm_partition **out,
+                      ehm_partition_stats *stats);
+/* copy the node store to HOST buffers sized from stats.nnodes:
+ * left/right/root_id/depth/cand int32[nnodes], closed uint8[nnodes],
+ * vertices f64[nnodes,(n+1),n], vcost f64[nnodes,n+1], vinput f64[nnodes,(n+1),nu] (scaled) */
+int ehm_partition_fetch(ehm_partition *t, int32_t *left, int32_t *right, int32_t *root_id,
+                        int32_t *depth, int32_t *cand, uint8_t *closed, double *vertices,
+                        double *vcost, double *vinput);
+int ehm_partition_free(ehm_partition *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -797,6 +797,12 @@ int ehmo_bar_e(ehmo_problem *pb, const double *R, const double *Vr, double *tsta
     return subopt;
 }
 
+/* min_{theta in R} V*_c(theta)  (min_over_simplex_for_this_delta, lib/oracle.py:75-79,276) */
+int ehmo_min_over_simplex(ehmo_problem *pb, const double *R, int c, double *val)
+{
+    return solve_simplex_qp(pb, c, R, NULL, 0, val, NULL);
+}
+
 /* bar_D_delta_R as a stand-alone call (brute force). */
 int ehmo_bar_d(ehmo_problem *pb, const double *R, const double *Vr, int cref,
                double *theta_star, double *Jv, double *Uv, int *var_small)

@@ -83,6 +83,9 @@ int ehmo_bar_e(ehmo_problem *pb, const double *R, const double *Vr, double *tsta
 int ehmo_bar_d(ehmo_problem *pb, const double *R, const double *Vr, int cand_ref,
                double *theta_star, double *Jv, double *Uv, int *var_small);
 
+/* min over the simplex of V*_c; returns 0 on success */
+int ehmo_min_over_simplex(ehmo_problem *pb, const double *R, int cand, double *val);
+
 /* geometry */
 void ehmo_split(int n, const double *R, double *S1, double *S2, int *ij);
 double ehmo_simplex_volume(int n, const double *R);

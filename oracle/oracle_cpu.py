@@ -53,6 +53,7 @@ def lib():
         L.ehmo_v_r.argtypes = [C.c_void_p, dp, dp, dp]
         L.ehmo_bar_e.argtypes = [C.c_void_p, dp, dp, dp]
         L.ehmo_bar_d.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, dp, dp, ip]
+        L.ehmo_min_over_simplex.argtypes = [C.c_void_p, dp, C.c_int, dp]
         L.ehmo_split.argtypes = [C.c_int, dp, dp, dp, ip]
         L.ehmo_simplex_volume.argtypes = [C.c_int, dp]
         L.ehmo_simplex_volume.restype = C.c_double
@@ -147,6 +148,11 @@ class CpuOracle:
         return (self.problem.commutation_from_index(c), th,
                 [(self.problem.u_scale * Uv[i], Jv[i], 0.0) for i in range(self.n + 1)],
                 bool(vs.value))
+
+    def min_over_simplex(self, R, cand):
+        v = C.c_double()
+        st = lib().ehmo_min_over_simplex(self._h, _dp(_f64(R)), int(cand), C.byref(v))
+        return v.value if st == 0 else None
 
     # ---- geometry -----------------------------------------------------------------------
     @staticmethod

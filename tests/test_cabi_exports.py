@@ -1,0 +1,30 @@
+"""The C-ABI library loads and exports every symbol include/ehm.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    import __graft_entry__ as ge
+    ge.build()
+    from explicit_hybrid_mpc_b200 import _capi
+    hdr = open(os.path.join(ROOT, 'include', 'ehm.h')).read()
+    names = set(re.findall(r'\b(ehm_[a-z_0-9]+)\s*\(', hdr))
+    assert len(names) >= 12
+    L = ctypes.CDLL(_capi.LIB_PATH)
+    for nm in sorted(names):
+        assert hasattr(L, nm), 'missing export ' + nm
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to run instead of falling back."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    from explicit_hybrid_mpc_b200.mpc_library import InvertedPendulumOnCart
+    from explicit_hybrid_mpc_b200.oracle import Oracle
+    import pytest
+    with pytest.raises(RuntimeError):
+        Oracle(InvertedPendulumOnCart(), 1.0, 1.0)

@@ -1,0 +1,117 @@
+"""GPU parity of the batched oracle sub-problems (through the C-ABI) against the CPU oracle.
+
+Tolerance: both sides converge the same convex programs to 1e-9 relative (gap + primal
+residual); values must agree to 1e-7 * max(1,|v|) and feasibility decisions exactly."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-7
+
+
+def _close(a, b):
+    return abs(a - b) <= RTOL * max(1.0, abs(a), abs(b))
+
+
+def test_point_batch_vs_cpu(pendulum, cpu_oracle, gpu_oracle):
+    rng = np.random.default_rng(1)
+    ts = pendulum.theta_scale
+    B = 600
+    theta = rng.uniform(-1, 1, size=(B, 4)) * ts
+    cand = rng.integers(0, gpu_oracle.ncand, size=B).astype(np.int32)
+    # make a good share feasible: reuse the argmin commutation of P_theta at some points
+    for b in range(0, B, 3):
+        d = cpu_oracle.P_theta(theta[b])[1]
+        if d is not None:
+            cand[b] = pendulum.problem.index_from_commutation(d)
+    J, u0, st = gpu_oracle.point_batch(theta, cand)
+    J, u0, st = J.cpu().numpy(), u0.cpu().numpy(), st.cpu().numpy()
+    nfeas = 0
+    for b in range(B):
+        ok = cpu_oracle.P_theta_delta(theta[b], int(cand[b]), check_feasibility=True)
+        assert (st[b] == 1) == ok, (b, st[b], ok)
+        if ok:
+            nfeas += 1
+            u_c, J_c, _ = cpu_oracle.P_theta_delta(theta[b], int(cand[b]))
+            assert _close(J[b], J_c), (b, J[b], J_c)
+            assert abs(u0[b, 0] * 20.0 - u_c[0]) <= 1e-5 * max(1.0, abs(u_c[0]))
+    assert nfeas > 100
+
+
+def test_p_theta_matches_cpu(pendulum, cpu_oracle, gpu_oracle):
+    ts = pendulum.theta_scale
+    for th in (np.array([0.3, 0.02, 0.5, 0.1]), 0.25 * ts * np.array([1, -1, 1, -1]),
+               np.array([-0.5, 0.05, -0.4, 0.2])):
+        u_g, d_g, J_g, _ = gpu_oracle.P_theta(th)
+        u_c, d_c, J_c, _ = cpu_oracle.P_theta(th)
+        assert np.array_equal(d_g, d_c)
+        assert _close(J_g, J_c)
+        assert abs(u_g[0] - u_c[0]) <= 1e-5 * max(1.0, abs(u_c[0]))
+
+
+def test_tstar_all_candidates(pendulum, pendulum_roots, cpu_oracle, gpu_oracle):
+    """bar_E's per-candidate epigraph optimum t*_c on two root simplices."""
+    for ridx in (0, 50):
+        R = pendulum_roots[ridx]
+        d, vx = cpu_oracle.V_R(R)
+        Vr = np.array([v[1] for v in vx])
+        sub_c, t_c = cpu_oracle.bar_E_delta_R(R, Vr, return_tstar=True)
+        t_g, _ = gpu_oracle._tstar_all(R, Vr)
+        t_g = t_g.cpu().numpy()
+        assert np.array_equal(np.isnan(t_c), np.isnan(t_g))
+        live = ~np.isnan(t_c)
+        assert live.sum() > 50
+        err = np.abs(t_c[live] - t_g[live]) / np.maximum(1.0, np.abs(t_c[live]))
+        assert err.max() <= RTOL, err.max()
+        assert gpu_oracle.bar_E_delta_R(R, Vr) == sub_c
+
+
+def test_v_r_and_bar_d(pendulum, pendulum_roots, cpu_oracle, gpu_oracle):
+    for ridx in (0, 30, 50):
+        R = pendulum_roots[ridx]
+        d_c, vx_c = cpu_oracle.V_R(R)
+        d_g, vx_g = gpu_oracle.V_R(R)
+        assert np.array_equal(d_c, d_g)
+        for (u1, J1, _), (u2, J2, _) in zip(vx_c, vx_g):
+            assert _close(J1, J2)
+        Vr = np.array([v[1] for v in vx_c])
+        r_c = cpu_oracle.bar_D_delta_R(R, Vr, d_c)
+        r_g = gpu_oracle.bar_D_delta_R(R, Vr, d_c)
+        assert (r_c[0] is None) == (r_g[0] is None)
+        if r_c[0] is not None:
+            assert np.array_equal(r_c[0], r_g[0])
+            assert np.allclose(r_c[1], r_g[1], rtol=0, atol=1e-5 * np.abs(R).max())
+            assert r_c[3] == r_g[3]
+            for (u1, J1, _), (u2, J2, _) in zip(r_c[2], r_g[2]):
+                assert _close(J1, J2)
+
+
+def test_min_over_simplex(pendulum, pendulum_roots, cpu_oracle, gpu_oracle):
+    from explicit_hybrid_mpc_b200._capi import SX_MINV
+    R = pendulum_roots[3]
+    d, _ = cpu_oracle.V_R(R)
+    c = pendulum.problem.index_from_commutation(d)
+    v_c = cpu_oracle.min_over_simplex(R, c)
+    v_g, _, st = gpu_oracle.simplex_batch(R[None], None, np.array([c], np.int32), SX_MINV, False)
+    assert int(st[0]) == 1 and _close(float(v_g[0]), v_c)
+
+
+def test_split_bit_exact(gpu_oracle, cpu_oracle):
+    import torch
+    from explicit_hybrid_mpc_b200 import _capi
+    rng = np.random.default_rng(7)
+    B, n = 512, 4
+    R = rng.standard_normal((B, n + 1, n))
+    # force ties: regular-ish simplices with repeated edge lengths
+    R[:64] = np.round(R[:64] * 2) / 2
+    Rt = torch.as_tensor(R).cuda()
+    S1, S2 = torch.empty_like(Rt), torch.empty_like(Rt)
+    ij = torch.empty(B, 2, dtype=torch.int32, device='cuda')
+    _capi.check(_capi.lib().ehm_split_batch(n, B, Rt.data_ptr(), S1.data_ptr(), S2.data_ptr(),
+                                            ij.data_ptr(), None))
+    S1, S2, ij = S1.cpu().numpy(), S2.cpu().numpy(), ij.cpu().numpy()
+    for b in range(B):
+        a1, a2, aij = cpu_oracle.split_along_longest_edge(R[b])
+        assert tuple(ij[b]) == tuple(aij)
+        assert np.array_equal(S1[b], a1) and np.array_equal(S2[b], a2)   # bit exact
