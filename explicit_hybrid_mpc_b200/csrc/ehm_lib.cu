@@ -393,3 +393,220 @@ extern "C" int ehm_read_counters(ehm_problem *p, int64_t *iters, int64_t *solves
     if (fails) *fails = (int64_t)h.fails;
     return EHM_OK;
 }
+
+// =========================================================================================
+// partition engine (host side)
+// =========================================================================================
+#include "ehm_partition.cuh"
+
+struct ehm_partition {
+    ehm_problem *pb = nullptr;
+    NodeStore ns{};
+    Frontier fr{};
+    WaveBuf wv{};
+    EccBuf eb{};
+    Ctl *dctl = nullptr;
+    Ctl hctl{};
+    std::vector<void *> allocs;
+    int n = 0, nu = 0;
+    template <typename T>
+    int alloc(T **p, size_t count)
+    {
+        cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) return fail(EHM_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        allocs.push_back((void *)*p);
+        return EHM_OK;
+    }
+    ~ehm_partition()
+    {
+        for (void *p : allocs) cudaFree(p);
+    }
+};
+
+namespace {
+
+template <int U, int NX, int MR>
+int run_partition_t(ehm_partition *t, int nroots, const ehm_partition_opts &o, ehm_partition_stats *stats)
+{
+    ehm_problem *p = t->pb;
+    const DevTables &tb = p->tb;
+    const int ncand = tb.ncand;
+    const size_t smem = (size_t)kWarpsPerCta * WarpWs<U, NX, MR>::kDoubles * sizeof(double);
+    auto kref = k_lcss_ref<U, NX, MR>;
+    auto keval = k_lcss_eval<U, NX, MR>;
+    auto kpts = k_lcss_points<U, NX, MR>;
+    auto kecc = k_ecc_points<U, NX, MR>;
+    int rc;
+    if ((rc = set_smem(kref, smem)) || (rc = set_smem(keval, smem)) || (rc = set_smem(kpts, smem)) ||
+        (rc = set_smem(kecc, smem)))
+        return rc;
+    const int gsolve = p->sm_count * 2, tsolve = 32 * kWarpsPerCta;
+    const int gaux = p->sm_count * 4, taux = 256;
+    cudaStream_t st = 0;
+    cudaEvent_t ev0, ev1;
+    EHM_CUDA(cudaEventCreate(&ev0));
+    EHM_CUDA(cudaEventCreate(&ev1));
+    DevCounters c0;
+    EHM_CUDA(cudaMemcpy(&c0, p->dcnt, sizeof c0, cudaMemcpyDeviceToHost));
+    EHM_CUDA(cudaEventRecord(ev0, st));
+    int64_t launches = 0, waves = 0;
+    Ctl &h = t->hctl;
+    // ---- ECC phase: roots (and their ECC descendants) -> L-CSS entries on the frontier ----
+    int q0 = 0;
+    while (q0 < h.necc_next && h.error == 0) {
+        const int ne = std::min(kEccWave, h.necc_next - q0);
+        k_reset_cursors<<<1, 32, 0, st>>>(t->dctl);
+        kecc<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->eb, q0, ne, 0, t->dctl, p->dcnt);
+        k_ecc_pick<NX><<<(ne * 32 + 127) / 128, 128, 0, st>>>(tb, t->eb, ne, t->dctl);
+        kecc<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->eb, q0, ne, 1, t->dctl, p->dcnt);
+        k_ecc_final<NX><<<(ne * 32 + 127) / 128, 128, 0, st>>>(tb, t->ns, t->fr, t->eb, q0, ne, t->dctl);
+        launches += 5;
+        EHM_CUDA(cudaMemcpyAsync(&h, t->dctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+        EHM_CUDA(cudaStreamSynchronize(st));
+        q0 += ne;
+        ++waves;
+        if (o.verbose) fprintf(stderr, "[ehm] ecc wave: queue %d/%d frontier %d nodes %d\n", q0, h.necc_next, h.ftop, h.nnodes);
+    }
+    // ---- L-CSS phase ------------------------------------------------------------------------
+    while (h.ftop > 0 && h.error == 0) {
+        if (o.node_budget > 0 && h.nnodes >= o.node_budget) break;
+        const int W = std::min(t->wv.W, h.ftop);
+        const int base = h.ftop - W;
+        k_pop<<<gaux, taux, 0, st>>>(t->fr, t->wv, base, W, ncand, t->dctl);
+        kref<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->wv, W, t->dctl, p->dcnt);
+        k_lcss_items<<<gaux, taux, 0, st>>>(t->ns, t->wv, W, ncand, t->dctl);
+        keval<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->wv, t->dctl, p->dcnt);
+        k_lcss_select<NX><<<gaux, taux, 0, st>>>(t->ns, t->wv, W, ncand, t->dctl);
+        kpts<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->wv, t->dctl, p->dcnt);
+        k_lcss_final<NX><<<gaux, taux, 0, st>>>(tb, t->ns, t->fr, t->wv, W, t->dctl);
+        launches += 7;
+        EHM_CUDA(cudaMemcpyAsync(&h, t->dctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+        EHM_CUDA(cudaStreamSynchronize(st));
+        ++waves;
+        if (o.verbose)
+            fprintf(stderr, "[ehm] wave %lld: popped %d items %d pitems %d -> frontier %d nodes %d leaves %d\n",
+                    (long long)waves, W, h.nitems, h.npitems, h.ftop, h.nnodes, h.nleaves);
+    }
+    EHM_CUDA(cudaEventRecord(ev1, st));
+    EHM_CUDA(cudaEventSynchronize(ev1));
+    EHM_CUDA(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    DevCounters c1;
+    EHM_CUDA(cudaMemcpy(&c1, p->dcnt, sizeof c1, cudaMemcpyDeviceToHost));
+    g_launches += launches;
+    if (stats) {
+        stats->nnodes = h.nnodes; stats->nleaves = h.nleaves;
+        stats->nsolves = (int64_t)(c1.solves - c0.solves); stats->niters = (int64_t)(c1.iters - c0.iters);
+        stats->nfail = (int64_t)(c1.fails - c0.fails); stats->nwaves = waves; stats->nlaunches = launches;
+        stats->open_left = h.ftop; stats->max_depth = h.max_depth; stats->device_ms = ms;
+    }
+    if (h.error == EHM_EINFEASIBLE) return fail(EHM_EINFEASIBLE, "STOP, Theta contains infeasible regions");
+    if (h.error == EHM_ECAPACITY) return fail(EHM_ECAPACITY, "node store or frontier capacity exhausted");
+    if (h.error == EHM_ENUMERIC) return fail(EHM_ENUMERIC, "midpoint vertex problem infeasible");
+    return EHM_OK;
+}
+
+}  // namespace
+
+extern "C" int ehm_partition_run(ehm_problem *p, int nroots, const double *roots,
+                                 const ehm_partition_opts *opts, ehm_partition **out,
+                                 ehm_partition_stats *stats)
+{
+    if (!p || nroots <= 0 || !roots || !out) return fail(EHM_EINVAL, "bad argument");
+    *out = nullptr;
+    ehm_partition_opts o{};
+    if (opts) o = *opts;
+    const DevTables &tb = p->tb;
+    const int n = tb.n, nu = tb.nu, ncand = tb.ncand;
+    const int W = o.wave > 0 ? o.wave : 4096;
+    const int64_t maxn = o.max_nodes > 0 ? o.max_nodes : (int64_t)1 << 22;
+    const int64_t fcap = o.max_frontier > 0 ? o.max_frontier : std::max<int64_t>(65536, 16 * (int64_t)W);
+    if (maxn > 0x7ffffff0ll || fcap > 0x7ffffff0ll || nroots > maxn) return fail(EHM_EINVAL, "capacity too large");
+    ehm_partition *t = new ehm_partition();
+    t->pb = p; t->n = n; t->nu = nu;
+    int rc = EHM_OK;
+    auto A = [&](int r) { if (rc == EHM_OK) rc = r; };
+    NodeStore &ns = t->ns;
+    ns.cap = (int)maxn;
+    A(t->alloc(&ns.verts, (size_t)maxn * (n + 1) * n)); A(t->alloc(&ns.vcost, (size_t)maxn * (n + 1)));
+    A(t->alloc(&ns.vinput, (size_t)maxn * (n + 1) * nu)); A(t->alloc(&ns.cand, maxn));
+    A(t->alloc(&ns.left, maxn)); A(t->alloc(&ns.right, maxn)); A(t->alloc(&ns.root_id, maxn));
+    A(t->alloc(&ns.depth, maxn)); A(t->alloc(&ns.closed, maxn));
+    Frontier &fr = t->fr;
+    fr.cap = (int)fcap;
+    A(t->alloc(&fr.node, fcap)); A(t->alloc(&fr.skip, fcap)); A(t->alloc(&fr.lb, (size_t)fcap * ncand));
+    WaveBuf &wv = t->wv;
+    wv.W = W;
+    const size_t WN = (size_t)W * ncand;
+    A(t->alloc(&wv.node, W)); A(t->alloc(&wv.skip, W)); A(t->alloc(&wv.lb, WN)); A(t->alloc(&wv.tref, W));
+    A(t->alloc(&wv.tval, WN)); A(t->alloc(&wv.titem, WN)); A(t->alloc(&wv.items, WN));
+    A(t->alloc(&wv.it_sol, WN * (n + 1))); A(t->alloc(&wv.sel, (size_t)W * kSelT)); A(t->alloc(&wv.nsel, W));
+    A(t->alloc(&wv.nimp, W)); A(t->alloc(&wv.conv, W)); A(t->alloc(&wv.ij, (size_t)2 * W));
+    A(t->alloc(&wv.vmid, (size_t)W * n));
+    const size_t PP = (size_t)W * ((kSelT + 1) * (n + 2) + 1);
+    A(t->alloc(&wv.pitems, PP)); A(t->alloc(&wv.ptJ, (size_t)W * (kSelT + 1) * (n + 2)));
+    A(t->alloc(&wv.ptU, (size_t)W * (kSelT + 1) * (n + 2) * nu)); A(t->alloc(&wv.ptS, (size_t)W * (kSelT + 1) * (n + 2)));
+    A(t->alloc(&wv.minv, W)); A(t->alloc(&wv.minv_st, W));
+    EccBuf &eb = t->eb;
+    A(t->alloc(&eb.queue, maxn)); A(t->alloc(&eb.J, (size_t)kEccWave * ncand * (n + 2)));
+    A(t->alloc(&eb.U, (size_t)kEccWave * ncand * (n + 1) * nu)); A(t->alloc(&eb.S, (size_t)kEccWave * ncand * (n + 2)));
+    A(t->alloc(&eb.pick, kEccWave));
+    A(t->alloc(&t->dctl, 1));
+    if (rc != EHM_OK) { delete t; return rc; }
+    // root nodes
+    {
+        std::vector<int> iz(nroots, -1), id(nroots), zero(nroots, 0);
+        for (int i = 0; i < nroots; ++i) id[i] = i;
+        std::vector<unsigned char> cz(nroots, 0);
+        cudaError_t e = cudaMemcpy(ns.verts, roots, (size_t)nroots * (n + 1) * n * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(ns.vcost, 0, (size_t)nroots * (n + 1) * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemset(ns.vinput, 0, (size_t)nroots * (n + 1) * nu * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(ns.cand, iz.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(ns.left, iz.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(ns.right, iz.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(ns.root_id, id.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(ns.depth, zero.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(ns.closed, cz.data(), nroots, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(eb.queue, id.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+        memset(&t->hctl, 0, sizeof(Ctl));
+        t->hctl.nnodes = nroots;
+        t->hctl.necc_next = nroots;
+        if (e == cudaSuccess) e = cudaMemcpy(t->dctl, &t->hctl, sizeof(Ctl), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { delete t; return fail(EHM_ECUDA, std::string("root upload: ") + cudaGetErrorString(e)); }
+    }
+    switch (p->cfg) {
+#define X(ID, UU, NN, MM) \
+    case ID: rc = run_partition_t<UU, NN, MM>(t, nroots, o, stats); break;
+        EHM_FOR_EACH_CFG(X)
+#undef X
+    default: rc = fail(EHM_EINVAL, "no kernel for this problem shape");
+    }
+    *out = t;  // returned even on error so the partial tree can be inspected
+    return rc;
+}
+
+extern "C" int ehm_partition_fetch(ehm_partition *t, int32_t *left, int32_t *right, int32_t *root_id,
+                                   int32_t *depth, int32_t *cand, uint8_t *closed, double *vertices,
+                                   double *vcost, double *vinput)
+{
+    if (!t) return fail(EHM_EINVAL, "null partition");
+    const size_t nn = (size_t)t->hctl.nnodes, n = t->n, nu = t->nu;
+    auto dl = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+        return dst ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) : cudaSuccess;
+    };
+    EHM_CUDA(dl(left, t->ns.left, nn * 4)); EHM_CUDA(dl(right, t->ns.right, nn * 4));
+    EHM_CUDA(dl(root_id, t->ns.root_id, nn * 4)); EHM_CUDA(dl(depth, t->ns.depth, nn * 4));
+    EHM_CUDA(dl(cand, t->ns.cand, nn * 4)); EHM_CUDA(dl(closed, t->ns.closed, nn));
+    EHM_CUDA(dl(vertices, t->ns.verts, nn * (n + 1) * n * 8)); EHM_CUDA(dl(vcost, t->ns.vcost, nn * (n + 1) * 8));
+    EHM_CUDA(dl(vinput, t->ns.vinput, nn * (n + 1) * nu * 8));
+    return EHM_OK;
+}
+
+extern "C" int ehm_partition_free(ehm_partition *t)
+{
+    delete t;
+    return EHM_OK;
+}

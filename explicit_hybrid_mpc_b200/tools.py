@@ -1,0 +1,87 @@
+"""
+Geometry helpers mirroring the reference's ``lib/tools.py:134-257`` (host side, NumPy).
+The partition loop does not call these -- the split runs inside the CUDA engine -- they
+exist so that code written against the reference keeps working and for the tests.
+"""
+import itertools
+import math
+
+import numpy as np
+
+from .tree import NodeData, Tree
+
+
+def simplex_volume(R):
+    """``lib/tools.py:134-150``: |det[v1-v0 ... vn-v0]| / n!"""
+    R = np.asarray(R, dtype=float)
+    M = np.column_stack([v - R[0] for v in R[1:]])
+    return abs(np.linalg.det(M)) / math.factorial(R.shape[0] - 1)
+
+
+def split_along_longest_edge(R):
+    """``lib/tools.py:224-257``.  The longest edge is the first maximum, in
+    ``itertools.combinations`` order, of the squared Euclidean length accumulated left to
+    right in fp64 (the rule the CUDA engine implements with non-fused mul/add)."""
+    R = np.asarray(R, dtype=float)
+    combos = list(itertools.combinations(range(R.shape[0]), 2))
+    best, idx = -1.0, 0
+    for q, (i, j) in enumerate(combos):
+        acc = 0.0
+        for k in range(R.shape[1]):
+            d = R[i, k] - R[j, k]
+            acc = acc + d * d
+        if acc > best:
+            best, idx = acc, q
+    i, j = combos[idx]
+    v_mid = (R[i] + R[j]) / 2.
+    S_1, S_2 = R.copy(), R.copy()
+    S_1[i] = v_mid
+    S_2[j] = v_mid
+    return S_1, S_2, (i, j)
+
+
+def delaunay(R):
+    """``lib/tools.py:152-189``: Delaunay triangulation of the polytope with vertex rows R
+    into a right-spine binary tree whose leaves are the simplices."""
+    import scipy.spatial as scs
+    R = np.asarray(R, dtype=float)
+    simplices = scs.Delaunay(R).simplices
+    return spine_from_simplices([R[s] for s in simplices], top_vertices=R)
+
+
+def spine_from_simplices(simplices, top_vertices=None):
+    """Right-spine tree over a list of root simplices (what ``delaunay`` +
+    ``join_triangulation`` produce, ``lib/tools.py:172-222``)."""
+    Nsx = len(simplices)
+    vol = sum(simplex_volume(s) for s in simplices)
+    root = Tree(NodeData(vertices=top_vertices if top_vertices is not None else simplices[0]))
+    if Nsx == 1:
+        root.data = NodeData(vertices=simplices[0])
+        return root, Nsx, vol
+    cursor = root
+    for i in range(Nsx - 1):
+        left = NodeData(vertices=simplices[i])
+        right = None if i < Nsx - 2 else NodeData(vertices=simplices[i + 1])
+        cursor.grow(left, right)
+        cursor = cursor.right
+    return root, Nsx, vol
+
+
+def join_triangulation(cursor, new_tree):
+    """``lib/tools.py:191-222``: append new_tree at the rightmost leaf of cursor."""
+    if cursor.is_leaf():
+        cursor.grow(cursor.data, None)
+        cursor.right = new_tree
+        new_tree.top = False
+        cursor.data = None
+    else:
+        join_triangulation(cursor.right, new_tree)
+
+
+def leaves(tree, location=''):
+    """Yield ``(location, node)`` for every leaf, depth first, left before right."""
+    if tree.is_leaf():
+        yield location, tree
+    else:
+        yield from leaves(tree.left, location + '0')
+        yield from leaves(tree.right, location + '1')

@@ -1,0 +1,114 @@
+"""Whole-tree parity: the device-resident partition loop (through the C-ABI) against the CPU
+oracle's serial ECC/L-CSS recursion on the same root simplices.
+
+Bar: identical tree topology, leaf vertex sets BIT-EXACT, identical
+commutations, vertex costs within 1e-6*max(1,|J|)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _walk(arr, node, path, out):
+    """(path, node) pairs of one subtree, iterative."""
+    stack = [(node, path)]
+    while stack:
+        i, p = stack.pop()
+        out[p] = i
+        if arr['left'][i] >= 0:
+            stack.append((arr['left'][i], p + '0'))
+            stack.append((arr['right'][i], p + '1'))
+
+
+def _by_path(arr, nroots):
+    """map 'root:path' -> node id"""
+    out = {}
+    roots = {}
+    for i in range(len(arr['left'])):
+        if arr['depth'][i] == 0:
+            roots[int(arr['root_id'][i])] = i
+    assert len(roots) == nroots
+    for r, i in roots.items():
+        sub = {}
+        _walk(arr, i, '', sub)
+        for p, j in sub.items():
+            out['%d:%s' % (r, p)] = j
+    return out
+
+
+def compare_trees(g, c, nroots):
+    pg, pc = _by_path(g, nroots), _by_path(c, nroots)
+    assert set(pg) == set(pc), 'tree topology differs (%d vs %d nodes)' % (len(pg), len(pc))
+    worst = 0.0
+    for key, i in pg.items():
+        j = pc[key]
+        assert (g['left'][i] < 0) == (c['left'][j] < 0), key
+        assert np.array_equal(g['vertices'][i], c['vertices'][j]), 'vertices not bit-exact at ' + key
+        assert int(g['cand'][i]) == int(c['cand'][j]), 'commutation differs at ' + key
+        assert int(g['closed'][i]) == int(c['closed'][j]), key
+        if g['cand'][i] >= 0:
+            d = np.abs(g['vcost'][i] - c['vcost'][j]) / np.maximum(1.0, np.abs(c['vcost'][j]))
+            worst = max(worst, d.max())
+            assert d.max() <= 1e-6, (key, d.max())
+            du = np.abs(g['vinput'][i] - c['vinput'][j]).max()
+            assert du <= 1e-4 * 20.0, (key, du)
+    return worst
+
+
+def _gpu_arrays(res):
+    return {k: getattr(res, k) for k in ('left', 'right', 'root_id', 'depth', 'cand', 'closed',
+                                         'vertices', 'vcost', 'vinput')}
+
+
+@pytest.mark.parametrize('sel', [[22], [44, 22], [0]])
+def test_tree_equals_cpu_oracle(sel, pendulum_roots, cpu_oracle, gpu_oracle):
+    from explicit_hybrid_mpc_b200.partition import partition
+    roots = pendulum_roots[sel]
+    res = partition(gpu_oracle, roots, wave=256)
+    assert res.stats['nfail'] == 0
+    cpu = cpu_oracle.partition(roots, nthreads=len(sel))
+    assert cpu['error'] == 0 and cpu['nfail'] == 0
+    assert res.stats['nleaves'] == cpu['nleaves']
+    worst = compare_trees(_gpu_arrays(res), cpu, len(sel))
+    print('nodes %d leaves %d worst rel cost diff %.2e' % (res.nnodes, res.stats['nleaves'], worst))
+
+
+def test_cpu_prune_equals_bruteforce(pendulum_roots, cpu_oracle):
+    """The inherited bounds only skip work: same tree with and without them (CPU oracle)."""
+    roots = pendulum_roots[[22]]
+    a = cpu_oracle.partition(roots, prune=True)
+    b = cpu_oracle.partition(roots, prune=False)
+    assert a['nsolves'] < b['nsolves']
+    compare_trees(a, b, 1)
+
+
+def test_full_partition_invariants(pendulum, pendulum_roots, gpu_oracle):
+    """BASELINE config 2 at full size (all 66 roots, eps_r=1.0): size-independent properties.
+    The leaves tile Theta (sum of leaf volumes = vol Theta, cf. lib/scheduler.py:257-260),
+    every leaf is closed, every vertex is a dyadic combination of root vertices inside its
+    root simplex, children halve their parent's volume."""
+    from explicit_hybrid_mpc_b200.partition import partition
+    from explicit_hybrid_mpc_b200.tools import simplex_volume
+    res = partition(gpu_oracle, pendulum_roots)
+    assert res.stats['nfail'] == 0
+    leaves = res.leaf_ids()
+    assert len(leaves) == res.stats['nleaves'] and len(leaves) > 10000
+    assert res.closed[leaves].all()
+    assert (res.cand[leaves] >= 0).all()
+    vol = sum(simplex_volume(res.vertices[i]) for i in leaves)
+    ts = pendulum.theta_scale
+    assert abs(vol - np.prod(2 * ts)) <= 1e-9 * np.prod(2 * ts)
+    # parent volume = 2 x child volume, on a sample
+    inner = np.nonzero(res.left >= 0)[0]
+    for i in inner[:: max(1, len(inner) // 500)]:
+        v = simplex_volume(res.vertices[i])
+        for ch in (res.left[i], res.right[i]):
+            assert abs(simplex_volume(res.vertices[ch]) - 0.5 * v) <= 1e-9 * v
+    # leaf costs are true optimal costs of the leaf's commutation (spot check through the
+    # batched kernel)
+    samp = leaves[:: max(1, len(leaves) // 300)]
+    th = res.vertices[samp].reshape(-1, 4)
+    cd = np.repeat(res.cand[samp], 5).astype(np.int32)
+    J, _, st = gpu_oracle.point_batch(th, cd)
+    assert (st.cpu().numpy() == 1).all()
+    assert np.allclose(J.cpu().numpy(), res.vcost[samp].reshape(-1), rtol=1e-7, atol=1e-7)
