@@ -21,6 +21,7 @@ EXPORTS = [
     'ehm_problem_create', 'ehm_problem_destroy', 'ehm_set_eps', 'ehm_num_candidates',
     'ehm_last_error', 'ehm_kernel_launches', 'ehm_qp_theta_delta_batch', 'ehm_simplex_batch',
     'ehm_split_batch', 'ehm_partition_run', 'ehm_partition_fetch', 'ehm_partition_free',
+    'ehm_read_counters', 'ehm_fp64_peak', 'ehm_hbm_peak',
 ]
 
 
@@ -45,7 +46,9 @@ class PartitionOpts(C.Structure):
 class PartitionStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ('nnodes', 'nleaves', 'nsolves', 'niters', 'nfail',
                                          'nwaves', 'nlaunches', 'open_left')] + \
-               [('max_depth', C.c_int), ('device_ms', C.c_double)]
+               [('max_depth', C.c_int), ('device_ms', C.c_double),
+                ('stage_ms', C.c_double * 8), ('stage_flops', C.c_double * 8),
+                ('stage_bytes', C.c_double * 8)]
 
 
 _lib = None
@@ -70,6 +73,8 @@ def lib():
         L.ehm_simplex_batch.argtypes = [vp, C.c_int, dp, dp, ip, C.c_int, C.c_int, dp, dp, ip, vp]
         L.ehm_split_batch.argtypes = [C.c_int, C.c_int, dp, dp, dp, ip, vp]
         L.ehm_read_counters.argtypes = [vp] + [C.POINTER(C.c_int64)] * 3
+        L.ehm_fp64_peak.argtypes = [C.POINTER(C.c_double)]
+        L.ehm_hbm_peak.argtypes = [C.c_int64, C.POINTER(C.c_double)]
         if hasattr(L, 'ehm_partition_run'):
             L.ehm_partition_run.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
                                             C.POINTER(PartitionOpts), C.POINTER(vp),

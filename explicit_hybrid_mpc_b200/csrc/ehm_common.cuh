@@ -33,6 +33,7 @@ struct DevCounters {
     unsigned long long iters;   // IPM iterations
     unsigned long long solves;  // IPM solves
     unsigned long long fails;   // numerical failures
+    double flops[8];            // algorithmic flops per pipeline stage (0 = batch API)
 };
 
 }  // namespace ehm

@@ -163,7 +163,8 @@ template <int NV, int MR, bool HASH>
 __device__ __noinline__ int ipm_solve(const double *__restrict__ Gs, const double *__restrict__ hs,
                                       unsigned act, const double *__restrict__ Hs,
                                       const double *__restrict__ fs, double *red,
-                                      double (&z)[NV], double &obj_out, int &iters_out, int lane)
+                                      double (&z)[NV], double &obj_out, int &iters_out, int lane,
+                                      double *flops_out = nullptr)
 {
     constexpr int MRP = 32 * MR;
     constexpr int NK = NV * (NV + 1) / 2;
@@ -359,6 +360,10 @@ __device__ __noinline__ int ipm_solve(const double *__restrict__ Gs, const doubl
     }
     obj_out = obj;
     iters_out = it;
+    // algorithmic flops (2 per FMA): K build m*NV(NV+1), six mat-vecs 12*m*NV, Cholesky NV^3/3,
+    // two triangular solve pairs 4*NV^2 -- per iteration
+    if (flops_out)
+        *flops_out += (double)it * (mact * (NV * (NV + 1) + 12.0 * NV) + NV * NV * NV / 3.0 + 4.0 * NV * NV);
     return status;
 }
 

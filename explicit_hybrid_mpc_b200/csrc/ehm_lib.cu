@@ -41,9 +41,10 @@ __device__ __forceinline__ long long next_item(DevCounters *cnt, int lane)
     return (long long)__shfl_sync(kFull, v, 0);
 }
 
-__device__ __forceinline__ void account(DevCounters *cnt, const SolveOut &o, int lane)
+__device__ __forceinline__ void account(DevCounters *cnt, const SolveOut &o, int lane, int stage = 0)
 {
     if (lane == 0) {
+        atomicAdd(&cnt->flops[stage], o.flops);
         atomicAdd(&cnt->iters, (unsigned long long)o.iters);
         atomicAdd(&cnt->solves, (unsigned long long)o.nsolves);
         if (o.status < 0) atomicAdd(&cnt->fails, 1ull);
@@ -62,7 +63,7 @@ k_point_batch(DevTables tb, int B, const double *__restrict__ theta, const int *
         const long long b = next_item(cnt, lane);
         if (b >= B) break;
         const int c = cand[b];
-        SolveOut o{0, 0.0, 0, 0};
+        SolveOut o{0, 0.0, 0, 0, 0.0};
         if (c >= 0 && c < tb.ncand)
             o = solve_point<U, NX, MR>(tb, c, theta + (size_t)b * NX, ws, u0 ? u0 + (size_t)b * tb.nu : nullptr, lane);
         account(cnt, o, lane);
@@ -87,7 +88,7 @@ k_simplex_batch(DevTables tb, int B, const double *__restrict__ R, const double 
         const long long b = next_item(cnt, lane);
         if (b >= B) break;
         const int c = cand[b];
-        SolveOut o{0, 0.0, 0, 0};
+        SolveOut o{0, 0.0, 0, 0, 0.0};
         if (c >= 0 && c < tb.ncand)
             o = solve_simplex<U, NX, MR>(tb, c, R + (size_t)b * (NX + 1) * NX,
                                          Vr ? Vr + (size_t)b * (NX + 1) : nullptr, mode,
@@ -468,25 +469,56 @@ int run_partition_t(ehm_partition *t, int nroots, const ehm_partition_opts &o, e
         if (o.verbose) fprintf(stderr, "[ehm] ecc wave: queue %d/%d frontier %d nodes %d\n", q0, h.necc_next, h.ftop, h.nnodes);
     }
     // ---- L-CSS phase ------------------------------------------------------------------------
+    cudaEvent_t sev[8];
+    for (auto &e : sev) EHM_CUDA(cudaEventCreate(&e));
+    double sms[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sbytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    {
+        float ems = 0;
+        EHM_CUDA(cudaEventRecord(sev[0], st));
+        EHM_CUDA(cudaEventSynchronize(sev[0]));
+        cudaEventElapsedTime(&ems, ev0, sev[0]);
+        sms[7] = ems;
+    }
     while (h.ftop > 0 && h.error == 0) {
         if (o.node_budget > 0 && h.nnodes >= o.node_budget) break;
         const int W = std::min(t->wv.W, h.ftop);
         const int base = h.ftop - W;
+        EHM_CUDA(cudaEventRecord(sev[0], st));
         k_pop<<<gaux, taux, 0, st>>>(t->fr, t->wv, base, W, ncand, t->dctl);
+        EHM_CUDA(cudaEventRecord(sev[1], st));
         kref<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->wv, W, t->dctl, p->dcnt);
+        EHM_CUDA(cudaEventRecord(sev[2], st));
         k_lcss_items<<<gaux, taux, 0, st>>>(t->ns, t->wv, W, ncand, t->dctl);
+        EHM_CUDA(cudaEventRecord(sev[3], st));
         keval<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->wv, t->dctl, p->dcnt);
+        EHM_CUDA(cudaEventRecord(sev[4], st));
         k_lcss_select<NX><<<gaux, taux, 0, st>>>(t->ns, t->wv, W, ncand, t->dctl);
+        EHM_CUDA(cudaEventRecord(sev[5], st));
         kpts<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->wv, t->dctl, p->dcnt);
+        EHM_CUDA(cudaEventRecord(sev[6], st));
         k_lcss_final<NX><<<gaux, taux, 0, st>>>(tb, t->ns, t->fr, t->wv, W, t->dctl);
+        EHM_CUDA(cudaEventRecord(sev[7], st));
         launches += 7;
+        const int ftop_before = base;
         EHM_CUDA(cudaMemcpyAsync(&h, t->dctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         EHM_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < 7; ++k) {
+            float ems = 0;
+            cudaEventElapsedTime(&ems, sev[k], sev[k + 1]);
+            sms[k] += ems;
+        }
+        // algorithmic HBM bytes of the streaming stages: pop moves W bound rows (read+write),
+        // items reads them and writes tval(8)+titem(4), final reads one row and writes one
+        // row per pushed entry
+        sbytes[0] += 2.0 * W * ncand * 4.0;
+        sbytes[2] += (double)W * ncand * 16.0;
+        sbytes[6] += (double)(h.ftop - ftop_before) * ncand * 8.0;
         ++waves;
         if (o.verbose)
             fprintf(stderr, "[ehm] wave %lld: popped %d items %d pitems %d -> frontier %d nodes %d leaves %d\n",
                     (long long)waves, W, h.nitems, h.npitems, h.ftop, h.nnodes, h.nleaves);
     }
+    for (auto &e : sev) cudaEventDestroy(e);
     EHM_CUDA(cudaEventRecord(ev1, st));
     EHM_CUDA(cudaEventSynchronize(ev1));
     EHM_CUDA(cudaGetLastError());
@@ -502,6 +534,9 @@ int run_partition_t(ehm_partition *t, int nroots, const ehm_partition_opts &o, e
         stats->nsolves = (int64_t)(c1.solves - c0.solves); stats->niters = (int64_t)(c1.iters - c0.iters);
         stats->nfail = (int64_t)(c1.fails - c0.fails); stats->nwaves = waves; stats->nlaunches = launches;
         stats->open_left = h.ftop; stats->max_depth = h.max_depth; stats->device_ms = ms;
+        for (int k = 0; k < 8; ++k) { stats->stage_ms[k] = sms[k]; stats->stage_bytes[k] = sbytes[k]; stats->stage_flops[k] = 0; }
+        stats->stage_flops[1] = c1.flops[1] - c0.flops[1]; stats->stage_flops[3] = c1.flops[2] - c0.flops[2];
+        stats->stage_flops[5] = c1.flops[3] - c0.flops[3]; stats->stage_flops[7] = c1.flops[4] - c0.flops[4];
     }
     if (h.error == EHM_EINFEASIBLE) return fail(EHM_EINFEASIBLE, "STOP, Theta contains infeasible regions");
     if (h.error == EHM_ECAPACITY) return fail(EHM_ECAPACITY, "node store or frontier capacity exhausted");
@@ -608,5 +643,89 @@ extern "C" int ehm_partition_fetch(ehm_partition *t, int32_t *left, int32_t *rig
 extern "C" int ehm_partition_free(ehm_partition *t)
 {
     delete t;
+    return EHM_OK;
+}
+
+// =========================================================================================
+// measurement helpers
+// =========================================================================================
+__global__ void k_dfma_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int ehm_fp64_peak(double *tflops)
+{
+    if (!tflops) return fail(EHM_EINVAL, "null");
+    int dev = 0, sms = 148;
+    EHM_CUDA(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 4, threads = 512, iters = 1 << 16;
+    double *d = nullptr;
+    EHM_CUDA(cudaMalloc((void **)&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        k_dfma_peak<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0) best = std::max(best, tf);
+    }
+    g_launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    EHM_CUDA(cudaGetLastError());
+    *tflops = best;
+    return EHM_OK;
+}
+
+__global__ void k_copy_peak(const double2 *__restrict__ src, double2 *__restrict__ dst, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+extern "C" int ehm_hbm_peak(int64_t bytes, double *gbs)
+{
+    if (!gbs || bytes < (1 << 20)) return fail(EHM_EINVAL, "bad argument");
+    const size_t n = (size_t)bytes / sizeof(double2);
+    double2 *a = nullptr, *b = nullptr;
+    EHM_CUDA(cudaMalloc((void **)&a, n * sizeof(double2)));
+    EHM_CUDA(cudaMalloc((void **)&b, n * sizeof(double2)));
+    EHM_CUDA(cudaMemset(a, 0, n * sizeof(double2)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_copy_peak<<<148 * 16, 512>>>(a, b, n);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0) best = std::max(best, 2.0 * n * sizeof(double2) / (ms * 1e-3) / 1e9);
+    }
+    g_launches += 5;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(a);
+    cudaFree(b);
+    EHM_CUDA(cudaGetLastError());
+    *gbs = best;
     return EHM_OK;
 }

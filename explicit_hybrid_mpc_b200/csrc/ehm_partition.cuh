@@ -165,7 +165,7 @@ k_lcss_ref(DevTables tb, NodeStore ns, WaveBuf wv, int W, Ctl *ctl, DevCounters 
         const SolveOut o = solve_simplex<U, NX, MR>(tb, ns.cand[nd], ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, false,
                                                     ws, nullptr, lane);
-        account(cnt, o, lane);
+        account(cnt, o, lane, 1);
         if (lane == 0) wv.tref[e] = (o.status == 1) ? o.val : INFINITY;
         __syncwarp();
     }
@@ -225,7 +225,7 @@ k_lcss_eval(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
         const SolveOut o = solve_simplex<U, NX, MR>(tb, ec.y, ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, true, ws,
                                                     wv.it_sol + (size_t)it * (NX + 1), lane);
-        account(cnt, o, lane);
+        account(cnt, o, lane, 2);
         if (lane == 0) {
             const size_t ix = (size_t)ec.x * tb.ncand + ec.y;
             if (o.status == 1) {
@@ -360,7 +360,7 @@ k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt
                 wv.ptS[slot] = o.status;
             }
         }
-        account(cnt, o, lane);
+        account(cnt, o, lane, 3);
         __syncwarp();
     }
 }
@@ -562,7 +562,7 @@ k_ecc_points(DevTables tb, NodeStore ns, EccBuf eb, int q0, int ne, int centroid
         const size_t slot = ((size_t)e * ncand + c) * (NX + 2) + i;
         double *up = (i <= NX) ? eb.U + (((size_t)e * ncand + c) * (NX + 1) + i) * tb.nu : nullptr;
         const SolveOut o = solve_point<U, NX, MR>(tb, c, thp, ws, up, lane);
-        account(cnt, o, lane);
+        account(cnt, o, lane, 4);
         if (lane == 0) {
             eb.J[slot] = o.val;
             eb.S[slot] = o.status;

@@ -51,6 +51,7 @@ struct SolveOut {
     double val;   // J, sigma*, t* or min V
     int iters;    // IPM iterations spent
     int nsolves;  // IPM solves spent
+    double flops; // algorithmic flops spent (see ipm_solve)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -65,7 +66,7 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
     constexpr int MRP = W::MRP;
     double *Gs = ws + W::oG, *hs = ws + W::oH, *Hs = ws + W::oHs, *fs = ws + W::oF,
            *red = ws + W::oRed;
-    SolveOut out{0, 0.0, 0, 0};
+    SolveOut out{0, 0.0, 0, 0, 0.0};
     const int MP = tb.MP, m = tb.m, Y = tb.Y;
     const double *Gc = tb.G + (size_t)c * U * MP, *Sc = tb.S + (size_t)c * NX * MP,
                  *gc = tb.g + (size_t)c * MP, *rc = tb.rho + (size_t)c * MP;
@@ -116,7 +117,7 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
         z[U] = s0 + 1.0;
         double obj;
         int it;
-        const int st = ipm_solve<U + 1, MR, false>(Gs, hs, act, Hs, fs, red, z, obj, it, lane);
+        const int st = ipm_solve<U + 1, MR, false>(Gs, hs, act, Hs, fs, red, z, obj, it, lane, &out.flops);
         out.iters += it;
         out.nsolves++;
         if (st != 0) {
@@ -155,7 +156,7 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
     for (int k = 0; k < U; ++k) z[k] = 0.0;
     double obj;
     int it;
-    const int st = ipm_solve<U, MR, true>(Gs, hs, act, Hs, fs, red, z, obj, it, lane);
+    const int st = ipm_solve<U, MR, true>(Gs, hs, act, Hs, fs, red, z, obj, it, lane, &out.flops);
     out.iters += it;
     out.nsolves++;
     if (st != 0) {
@@ -187,7 +188,7 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
     double *Gs = ws + W::oG, *hs = ws + W::oH, *Hs = ws + W::oHs, *fs = ws + W::oF,
            *red = ws + W::oRed, *Ms = ws + W::oM, *Ts = ws + W::oT, *MTs = ws + W::oMT,
            *Rs = ws + W::oR, *Es = ws + W::oE, *Vs = ws + W::oV;
-    SolveOut out{0, 0.0, 0, 0};
+    SolveOut out{0, 0.0, 0, 0, 0.0};
     const int MP = tb.MP, m = tb.m;
     const double *Gc = tb.G + (size_t)c * U * MP, *Sc = tb.S + (size_t)c * NX * MP,
                  *gc = tb.g + (size_t)c * MP, *rc = tb.rho + (size_t)c * MP;
@@ -307,7 +308,7 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         z[NB] = s0 + 1.0;
         double obj;
         int it;
-        const int st = ipm_solve<NVS, MR, false>(Gs, hs, act1, Hs, fs, red, z, obj, it, lane);
+        const int st = ipm_solve<NVS, MR, false>(Gs, hs, act1, Hs, fs, red, z, obj, it, lane, &out.flops);
         out.iters += it;
         out.nsolves++;
         if (st != 0) {
@@ -379,14 +380,14 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         double z[NVS];
 #pragma unroll
         for (int k = 0; k < NVS; ++k) z[k] = 0.0;
-        st = ipm_solve<NVS, MR, true>(Gs, hs, act, Hs, fs, red, z, obj, it, lane);
+        st = ipm_solve<NVS, MR, true>(Gs, hs, act, Hs, fs, red, z, obj, it, lane, &out.flops);
 #pragma unroll
         for (int k = 0; k < NVS; ++k) zsol[k] = z[k];
     } else {
         double z[NB];
 #pragma unroll
         for (int k = 0; k < NB; ++k) z[k] = 0.0;
-        st = ipm_solve<NB, MR, true>(Gs, hs, act, Hs, fs, red, z, obj, it, lane);
+        st = ipm_solve<NB, MR, true>(Gs, hs, act, Hs, fs, red, z, obj, it, lane, &out.flops);
 #pragma unroll
         for (int k = 0; k < NB; ++k) zsol[k] = z[k];
         zsol[NB] = 0.0;

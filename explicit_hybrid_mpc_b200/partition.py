@@ -107,6 +107,7 @@ def partition(oracle, roots, wave=0, max_nodes=0, max_frontier=0, node_budget=0,
             L.ehm_partition_free(h)
     wall = time.perf_counter() - t0
     arr['vinput'] = arr['vinput'] * oracle.pb.u_scale
-    st = {k: getattr(stats, k) for k, _ in _capi.PartitionStats._fields_}
+    st = {k: (list(getattr(stats, k)) if k.startswith('stage_') else getattr(stats, k))
+          for k, _ in _capi.PartitionStats._fields_}
     st['wall_s'] = wall
     return PartitionResult(arr, st, oracle.pb)

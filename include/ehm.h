@@ -107,6 +107,12 @@ typedef struct {
     int64_t open_left;     /* frontier entries left when a node_budget stopped the run      */
     int max_depth;
     double device_ms;      /* CUDA-event time of the whole loop                            */
+    /* per pipeline stage, summed over waves (CUDA events on the launching stream):
+     * 0 pop, 1 lcss_ref, 2 lcss_items, 3 lcss_eval, 4 lcss_select, 5 lcss_points,
+     * 6 lcss_final, 7 the ECC phase */
+    double stage_ms[8];
+    double stage_flops[8]; /* algorithmic fp64 flops of the solve stages (1,3,5,7)         */
+    double stage_bytes[8]; /* algorithmic HBM bytes of the streaming stages (0,2,6)        */
 } ehm_partition_stats;
 
 typedef struct ehm_partition ehm_partition;
@@ -122,6 +128,14 @@ int ehm_partition_fetch(ehm_partition *t, int32_t *left, int32_t *right, int32_t
                         int32_t *depth, int32_t *cand, uint8_t *closed, double *vertices,
                         double *vcost, double *vinput);
 int ehm_partition_free(ehm_partition *t);
+
+/* ---- measurement helpers (bench.py) --------------------------------------------------- */
+/* counters since problem creation */
+int ehm_read_counters(ehm_problem *p, int64_t *iters, int64_t *solves, int64_t *fails);
+/* dependent-free DFMA loop on every SM: the fp64 FMA roofline denominator, in TFLOP/s */
+int ehm_fp64_peak(double *tflops);
+/* STREAM-style device copy of `bytes` bytes: GB/s (read+write counted) */
+int ehm_hbm_peak(int64_t bytes, double *gbs);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,85 @@
+"""Pin the CPU oracle (and the pendulum problem lowering) against tests/golden/
+pendulum_golden.json: solutions of the REFERENCE-FORM problems -- built by the reference's own
+lib/mpc_library.py code, solved by SciPy HiGHS / SLSQP (see tests/golden/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+
+from conftest import GOLDEN
+
+G = json.load(open(os.path.join(GOLDEN, 'pendulum_golden.json')))
+
+
+def test_fixed_delta_problems(pendulum, cpu_oracle):
+    nfat = nthin = 0
+    for g in G['fixed']:
+        th, c = np.array(g['theta']), g['cand']
+        ok = cpu_oracle.P_theta_delta(th, c, check_feasibility=True)
+        if not g['feasible'] or g['margin'] < 1e-9:
+            # infeasible, or feasible only on a measure-zero slice (excluded by the canonical
+            # interior-margin rule TAU_INT)
+            assert not ok, g
+            nthin += 1
+        elif g['margin'] > 1e-5:
+            assert ok, g
+            nfat += 1
+            if g.get('J') is not None:
+                u0, J, _ = cpu_oracle.P_theta_delta(th, c)
+                assert abs(J - g['J']) <= 2e-6 * max(1.0, abs(g['J'])), (g, J)
+                assert abs(u0[0] - g['u0']) <= 2e-3 * max(1.0, abs(g['u0'])), (g, u0)
+    assert nfat >= 30 and nthin >= 20
+
+
+def test_micp_feasibility_points(pendulum, cpu_oracle):
+    """P_theta(check_feasibility=True): HiGHS branch & bound over binary delta on the
+    reference-form MILP vs enumeration in the oracle."""
+    for g in G['milp_point']:
+        th = np.array(g['theta'])
+        ok = cpu_oracle.P_theta(th, check_feasibility=True)
+        if not g['feasible']:
+            assert not ok, g
+        else:
+            # the commutation HiGHS found must be accepted by the oracle unless it is thin
+            c = pendulum.problem.index_from_commutation(np.array(g['delta']))
+            assert c >= 0
+            if cpu_oracle.P_theta_delta(th, c, check_feasibility=True):
+                assert ok
+
+
+def test_v_r_feasibility_simplices(pendulum, pendulum_roots, cpu_oracle):
+    for g in G['milp_simplex']:
+        R = pendulum_roots[g['root']]
+        d, vx = cpu_oracle.V_R(R)
+        assert (d is not None) == g['feasible']
+        # the oracle's canonical choice is feasible at every vertex by construction; it must
+        # be one-hot like every solution of the reference MILP (sum z[k] == 1)
+        assert np.allclose(np.asarray(d).reshape(5, 5).sum(axis=1), 1.0)
+        assert np.allclose(np.array(g['delta']).reshape(5, 5).sum(axis=1), 1.0)
+
+
+def test_problem_lowering_matches_appendix_a(pendulum):
+    """Spot values of the re-derived linearisation / discretisation."""
+    A, B, w = pendulum.A_d, pendulum.B_d, pendulum.w_d
+    assert abs(A[0][1, 1] - 1.0213246230) < 1e-9 and abs(A[0][2, 1] + 0.29604221141) < 1e-9
+    assert np.allclose(B[0], [0.0050040885, -0.0016725776, 0.1001636561, -0.0335699384], atol=1e-9)
+    assert np.allclose(w[2], [-0.0102104742, 0.0034127716, -0.2043711966, 0.068495202], atol=1e-9)
+    assert abs(pendulum.P[1, 1] - 2699.666188493) < 1e-5
+    assert np.array_equal(B[4], np.zeros(4)) and np.array_equal(w[4], np.zeros(4))
+
+
+def test_split_matches_reference_rule(cpu_oracle):
+    """tools.split_along_longest_edge: first maximum in itertools.combinations order."""
+    import itertools
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        R = np.round(rng.standard_normal((5, 4)) * 4) / 4     # many exact ties
+        S1, S2, ij = cpu_oracle.split_along_longest_edge(R)
+        combos = list(itertools.combinations(range(5), 2))
+        k = int(np.argmax([np.linalg.norm(R[a] - R[b]) ** 2 for a, b in combos]))
+        # np.linalg.norm may differ in the last bit; the oracle's rule is the exact-sum one
+        d2 = [sum((R[a, q] - R[b, q]) ** 2 for q in range(4)) for a, b in combos]
+        assert ij == combos[int(np.argmax(d2))]
+        assert d2[k] == max(d2)
+        mid = (R[ij[0]] + R[ij[1]]) / 2
+        assert np.array_equal(S1[ij[0]], mid) and np.array_equal(S2[ij[1]], mid)
