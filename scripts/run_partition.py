@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..'))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--eps-a', type=float, default=27.96235132870629)
+    ap.add_argument('--eps-a', type=float, default=19.21220798973866)
     ap.add_argument('--eps-r', type=float, default=1.0)
     ap.add_argument('--roots', type=str, default='all')
     ap.add_argument('--wave', type=int, default=0)

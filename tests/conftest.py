@@ -30,10 +30,10 @@ def pendulum_roots():
 def cpu_oracle(pendulum):
     """The CPU oracle (test infrastructure) at the eps of BASELINE config 2."""
     from oracle.oracle_cpu import CpuOracle
-    return CpuOracle(pendulum.problem, 27.96235132870629, 1.0, pendulum.theta_scale)
+    return CpuOracle(pendulum.problem, 19.21220798973866, 1.0, pendulum.theta_scale)
 
 
 @pytest.fixture(scope='session')
 def gpu_oracle(pendulum):
     from explicit_hybrid_mpc_b200.oracle import Oracle
-    return Oracle(pendulum, 27.96235132870629, 1.0)
+    return Oracle(pendulum, 19.21220798973866, 1.0)
