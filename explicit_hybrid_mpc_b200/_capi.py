@@ -21,7 +21,9 @@ EXPORTS = [
     'ehm_problem_create', 'ehm_problem_destroy', 'ehm_set_eps', 'ehm_num_candidates',
     'ehm_last_error', 'ehm_kernel_launches', 'ehm_qp_theta_delta_batch', 'ehm_simplex_batch',
     'ehm_split_batch', 'ehm_partition_run', 'ehm_partition_fetch', 'ehm_partition_free',
-    'ehm_read_counters', 'ehm_fp64_peak', 'ehm_hbm_peak',
+    'ehm_read_counters', 'ehm_fp64_peak', 'ehm_hbm_peak', 'ehm_partition_create',
+    'ehm_partition_advance', 'ehm_partition_export', 'ehm_partition_import',
+    'ehm_partition_fetch_origin', 'ehm_partition_set_root_ids',
 ]
 
 
@@ -81,6 +83,13 @@ def lib():
                                             C.POINTER(PartitionStats)]
             L.ehm_partition_fetch.argtypes = [vp] + [vp] * 9
             L.ehm_partition_free.argtypes = [vp]
+            L.ehm_partition_create.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
+                                               C.POINTER(PartitionOpts), C.POINTER(vp)]
+            L.ehm_partition_advance.argtypes = [vp, C.c_int64, C.POINTER(PartitionStats)]
+            L.ehm_partition_export.argtypes = [vp, C.c_int, vp, vp, vp]
+            L.ehm_partition_import.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+            L.ehm_partition_fetch_origin.argtypes = [vp, vp]
+            L.ehm_partition_set_root_ids.argtypes = [vp, C.c_int, vp]
         _lib = L
     return _lib
 

@@ -5,17 +5,22 @@
 // held entirely in shared memory + registers.  It replaces one `.solve()` of the
 // reference (CVXPY -> MOSEK, lib/oracle.py:131,134,166,169,203,276,305,350).
 //
-// Mapping to the hardware
-//   * lane L owns rows L, L+32, ... (MR of them): slack s, multiplier lam and the step
-//     vectors live in registers; G is stored column-major in shared memory so that the 32
-//     lanes read 32 consecutive doubles (conflict free, 256 B per LDS.64 wavefront pair).
+// Mapping to the hardware (version 2 -- sized for the instruction cache):
+//   * lane L owns rows L, L+32, ...; G is column-major in shared memory (32 lanes read 32
+//     consecutive doubles: conflict free); the per-row state (slack s, multiplier lam and the
+//     two step vectors) also lives in shared memory so that the row loops can stay ROLLED.
+//     The first version kept that state in registers, which forced a 7x unroll of every
+//     row pass: 25k SASS instructions, and ncu showed the warps stalled on instruction
+//     fetch (stall_no_instruction 5.5 per issue, profiles/README.md).  The hot loop is now
+//     ~1.5k instructions and fits the 32 KB L1.5 instruction cache.
 //   * the normal matrix K = H + G' diag(lam/s) G is accumulated per lane in NV(NV+1)/2
-//     registers and combined with a recursive-halving reduce-scatter (31 or 62 shuffles
-//     instead of 5*NK), the packed result is exchanged through a 64-double scratch line.
-//   * every lane then factors K redundantly in registers (fully unrolled Cholesky, static
-//     indexing) -- SIMT makes the redundancy free and avoids any further exchange for the
-//     two triangular solves of the predictor and the corrector.
-//   * step length = warp-shuffle min reduction.
+//     registers (static indices) and combined with a recursive-halving reduce-scatter
+//     (62 shuffles instead of 5*55), exchanged through a 64-double scratch line.
+//   * Cholesky is lane-parallel: lane i holds row i of K in registers, column j is formed
+//     with j shuffle broadcasts; the factor is then replicated into every lane's registers so
+//     that the two triangular solves of the predictor / corrector are shuffle-free.
+//   * predictor and corrector share one code path (a 2-trip loop), step lengths are
+//     warp-shuffle min reductions.
 //
 // The numerical method is, by specification, the one of oracle/ehm_oracle.c:qp_solve
 // (Mehrotra predictor-corrector in the CVXOPT/ECOS form: sigma=(1-alpha_aff)^3, residuals
@@ -98,272 +103,301 @@ __device__ __forceinline__ void warp_reduce_to_smem(double (&v)[P], double *out,
 // Packed lower-triangular index.
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// In-register Cholesky of the packed SPD matrix (lower).  inv[j] = 1/L_jj.
-// Pivot guard as in oracle/ehm_oracle.c:cholesky.  Returns false on NaN/Inf.
-template <int NV>
-__device__ __forceinline__ bool chol_packed(double (&L)[NV * (NV + 1) / 2], double (&inv)[NV])
+// Guarded pivot of the Cholesky factorisation (oracle/ehm_oracle.c:cholesky): returns
+// (sqrt(d), 1/sqrt(d)); a pivot that collapsed below 1e-13 of its own original diagonal
+// freezes the direction.
+__device__ __noinline__ double2 chol_pivot(double d, double d0)
 {
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const double d0 = L[tri(j, j)];
-        double d = d0;
-#pragma unroll
-        for (int k = 0; k < j; ++k) d = fma(-L[tri(j, k)], L[tri(j, k)], d);
-        if (!isfinite(d)) ok = false;
-        if (d <= 1e-13 * d0 || d0 <= 0.0) d = 1e100;
-        d = sqrt(d);
-        const double id = 1.0 / d;
-        L[tri(j, j)] = d;
-        inv[j] = id;
-#pragma unroll
-        for (int i = j + 1; i < NV; ++i) {
-            double v = L[tri(i, j)];
-#pragma unroll
-            for (int k = 0; k < j; ++k) v = fma(-L[tri(i, k)], L[tri(j, k)], v);
-            L[tri(i, j)] = v * id;
-        }
-    }
-    return ok;
+    if (d <= 1e-13 * d0 || d0 <= 0.0) d = 1e100;
+    const double sd = sqrt(d);
+    return make_double2(sd, 1.0 / sd);
 }
 
-template <int NV>
-__device__ __forceinline__ void chol_solve(const double (&L)[NV * (NV + 1) / 2],
-                                           const double (&inv)[NV], double (&b)[NV])
-{
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double v = b[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) v = fma(-L[tri(i, k)], b[k], v);
-        b[i] = v * inv[i];
-    }
-#pragma unroll
-    for (int i = NV - 1; i >= 0; --i) {
-        double v = b[i];
-#pragma unroll
-        for (int k = i + 1; k < NV; ++k) v = fma(-L[tri(k, i)], b[k], v);
-        b[i] = v * inv[i];
-    }
-}
-
-struct IpmStats {
-    int iters;
+// Per-warp shared-memory block of the solver (offsets in doubles from the block base).
+template <int NV, int MR>
+struct IpmWs {
+    static constexpr int MRP = 32 * MR;
+    static constexpr int oG = 0;                 // G, column-major [NV][MRP]
+    static constexpr int oH = oG + NV * MRP;     // h
+    static constexpr int oS = oH + MRP;          // slack
+    static constexpr int oL = oS + MRP;          // multiplier
+    static constexpr int oA = oL + MRP;          // rp / ds
+    static constexpr int oB = oA + MRP;          // ds.dl / rc / dl
+    static constexpr int oHs = oB + MRP;         // Hessian NV*NV row-major (zeros for an LP)
+    static constexpr int oF = oHs + NV * NV;     // f (16)
+    static constexpr int oZ = oF + 16;           // z in/out (16)
+    static constexpr int oRed = oZ + 16;         // reduction scratch / packed K / packed L (64)
+    static constexpr int oOut = oRed + 64;       // [0] objective [1] iterations [2] flops (8)
+    static constexpr int kDoubles = oOut + 8;
 };
 
-// Solve  min 0.5 z'Hz + f'z  s.t.  G z <= h  with one warp.
-//   Gs   : shared, column-major, column k at Gs + k*MRP, MRP = 32*MR rows (pad rows unused)
-//   hs   : shared, MRP
-//   act  : bit j set <=> row lane+32*j takes part (normalised, non-constant row)
-//   Hs   : shared, NV*NV row-major (ignored when !HASH), fs: shared NV
-//   red  : shared scratch, >= 64 doubles, private to the warp
-//   z    : in = primal start, out = solution (replicated in every lane)
-// returns 0 converged, 1 iteration limit, 2 numerical breakdown.
-template <int NV, int MR, bool HASH>
-__device__ __noinline__ int ipm_solve(const double *__restrict__ Gs, const double *__restrict__ hs,
-                                      unsigned act, const double *__restrict__ Hs,
-                                      const double *__restrict__ fs, double *red,
-                                      double (&z)[NV], double &obj_out, int &iters_out, int lane,
-                                      double *flops_out = nullptr)
+// Solve  min 0.5 z'Hz + f'z  s.t.  G z <= h  with one warp.  `w` = base of an IpmWs block:
+// G, h, Hs, f and the primal start z must be filled in; act: bit j set <=> row lane+32*j takes
+// part (normalised, non-constant row).  On return z holds the solution, out[0..2] the
+// objective / iteration count / algorithmic flops.  returns 0 converged, 1 iteration limit,
+// 2 numerical breakdown.
+template <int NV, int MR>
+__device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
 {
-    constexpr int MRP = 32 * MR;
+    using W = IpmWs<NV, MR>;
+    constexpr int MRP = W::MRP;
     constexpr int NK = NV * (NV + 1) / 2;
     constexpr int PK = pow2_ge(NK);
     constexpr int PV = pow2_ge(NV);
-    double s[MR], lam[MR], a[MR], b[MR];
-    double f[NV];
+    const double *__restrict__ Gs = w + W::oG;
+    const double *__restrict__ hs = w + W::oH;
+    double *sv = w + W::oS, *lv = w + W::oL, *av = w + W::oA, *bv = w + W::oB;
+    const double *__restrict__ Hs = w + W::oHs;
+    double *red = w + W::oRed;
+    double z[NV], f[NV];
     double fmx = 0.0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        f[k] = fs[k];
+        f[k] = w[W::oF + k];
+        z[k] = w[W::oZ + k];
         fmx = fmax(fmx, fabs(f[k]));
     }
     const double mact = warp_sum((double)__popc(act));
-#pragma unroll
-    for (int j = 0; j < MR; ++j) {
-        const int r = lane + 32 * j;
-        if (act >> j & 1u) {
-            double gz = 0.0;
-#pragma unroll
-            for (int k = 0; k < NV; ++k) gz = fma(Gs[k * MRP + r], z[k], gz);
-            s[j] = fmax(hs[r] - gz, 1.0);
-            lam[j] = 1.0 / s[j];
-        } else {
-            s[j] = 1.0;
-            lam[j] = 0.0;
-        }
-        a[j] = 0.0;
-        b[j] = 0.0;
-    }
-    int status = 1, it = 0;
-    double rho = 1.0, rd0 = 0.0, obj = 0.0;
-    for (it = 0; it <= EHM_MAX_ITER; ++it) {
-        // ---- residuals + normal matrix in one pass over G -------------------------------
-        double gl[PV], acc[PK];
+    // ---- centred start + initial dual residual rd0 = |H z0 + f + G' lam0| -----------------
+    double rd0;
+    {
+        double gl[PV];
 #pragma unroll
         for (int k = 0; k < PV; ++k) gl[k] = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < MR; ++j) {
+            if (!(act >> j & 1u)) continue;
+            const int r = lane + 32 * j;
+            double g[NV], gz = 0.0;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                g[k] = Gs[k * MRP + r];
+                gz = fma(g[k], z[k], gz);
+            }
+            const double s = fmax(hs[r] - gz, 1.0);
+            const double l = 1.0 / s;
+            sv[r] = s;
+            lv[r] = l;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) gl[k] = fma(g[k], l, gl[k]);
+        }
+        warp_reduce_to_smem<PV>(gl, red, NV, lane);
+        double m = 0.0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double hz = f[k] + red[k];
+#pragma unroll
+            for (int l = 0; l < NV; ++l) hz = fma(Hs[k * NV + l], z[l], hz);
+            m = fmax(m, fabs(hz));
+        }
+        rd0 = m;
+        __syncwarp();
+    }
+    int status = 1, it = 0;
+    double rho = 1.0, obj = 0.0;
+#pragma unroll 1
+    for (it = 0; it <= EHM_MAX_ITER; ++it) {
+        // ---- pass A: primal residual, gap, normal matrix ------------------------------------
+        double acc[PK];
 #pragma unroll
         for (int k = 0; k < PK; ++k) acc[k] = 0.0;
         double mu = 0.0, rpm = 0.0, lmx = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < MR; ++j) {
-            if (act >> j & 1u) {
-                const int r = lane + 32 * j;
-                double g[NV], gz = 0.0;
+            if (!(act >> j & 1u)) continue;
+            const int r = lane + 32 * j;
+            double g[NV], gz = 0.0;
 #pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    g[k] = Gs[k * MRP + r];
-                    gz = fma(g[k], z[k], gz);
-                }
-                const double rp = gz + s[j] - hs[r];
-                a[j] = rp;
-                rpm = fmax(rpm, fabs(rp));
-                mu = fma(s[j], lam[j], mu);
-                lmx = fmax(lmx, lam[j]);
-                const double w = lam[j] / s[j];
+            for (int k = 0; k < NV; ++k) {
+                g[k] = Gs[k * MRP + r];
+                gz = fma(g[k], z[k], gz);
+            }
+            const double s = sv[r], l = lv[r];
+            const double rp = gz + s - hs[r];
+            av[r] = rp;
+            rpm = fmax(rpm, fabs(rp));
+            mu = fma(s, l, mu);
+            lmx = fmax(lmx, l);
+            const double wt = l / s;
 #pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    gl[k] = fma(g[k], lam[j], gl[k]);
-                    const double gw = w * g[k];
+            for (int k = 0; k < NV; ++k) {
+                const double gw = wt * g[k];
 #pragma unroll
-                    for (int l = 0; l <= k; ++l) acc[tri(k, l)] = fma(gw, g[l], acc[tri(k, l)]);
-                }
+                for (int q = 0; q <= k; ++q) acc[tri(k, q)] = fma(gw, g[q], acc[tri(k, q)]);
             }
         }
         mu = warp_sum(mu);
         rpm = warp_max(rpm);
         lmx = warp_max(lmx);
-        warp_reduce_to_smem<PV>(gl, red, NV, lane);
-        double rd[NV], rdm = 0.0, zm = 0.0;
-        obj = 0.0;
+        // (H z + f): lane k forms row k, exchanged through the scratch line
+        double hzf[NV];
+        {
+            if (lane < NV) {
+                double v = w[W::oF + lane];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double hz = 0.0;
-            if (HASH) {
-#pragma unroll
-                for (int l = 0; l < NV; ++l) hz = fma(Hs[k * NV + l], z[l], hz);
+                for (int q = 0; q < NV; ++q) v = fma(Hs[lane * NV + q], z[q], v);
+                red[lane] = v;
             }
-            obj += z[k] * (f[k] + 0.5 * hz);
-            rd[k] = f[k] + hz + red[k];
-            rdm = fmax(rdm, fabs(rd[k]));
-            zm = fmax(zm, fabs(z[k]));
-        }
-        __syncwarp();
-        if (it == 0) rd0 = rdm;
-        if (!isfinite(mu) || !isfinite(rdm) || !isfinite(rpm)) {
-            status = 2;
-            break;
-        }
-        if (rpm <= EHM_TOL_IPM * (1.0 + zm) && rho * rd0 <= EHM_TOL_IPM * (1.0 + fmx + lmx) &&
-            rdm <= EHM_TOL_DUAL * (1.0 + fmx + lmx) && mu <= EHM_TOL_IPM * (1.0 + fabs(obj))) {
-            status = 0;
-            break;
+            __syncwarp();
+            double zm = 0.0;
+            obj = 0.0;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                hzf[k] = red[k];
+                obj = fma(z[k], 0.5 * (hzf[k] + f[k]), obj);
+                zm = fmax(zm, fabs(z[k]));
+            }
+            __syncwarp();
+            if (!isfinite(mu) || !isfinite(rpm) || !isfinite(obj)) {
+                status = 2;
+                break;
+            }
+            if (rpm <= EHM_TOL_IPM * (1.0 + zm) && rho * rd0 <= EHM_TOL_IPM * (1.0 + fmx + lmx) &&
+                mu <= EHM_TOL_IPM * (1.0 + fabs(obj))) {
+                status = 0;
+                break;
+            }
         }
         if (it == EHM_MAX_ITER) break;
         const double mu_mean = mu / mact;
-        // ---- factor K ---------------------------------------------------------------------
+        // ---- K -> packed scratch -> lane-parallel Cholesky -> replicated factor --------------
         warp_reduce_to_smem<PK>(acc, red, NK, lane);
         double L[NK], inv[NV];
+        {
+            double Lr[NV], d0 = 1.0;
+            const int li = lane < NV ? lane : 0;
 #pragma unroll
-        for (int k = 0; k < NV; ++k)
+            for (int k = 0; k < NV; ++k)
+                Lr[k] = (lane < NV && k <= lane) ? red[tri(li, k)] + Hs[li * NV + k] : 0.0;
+            if (lane < NV) d0 = red[tri(li, li)] + Hs[li * NV + li];
+            __syncwarp();
+            bool bad = false;
 #pragma unroll
-            for (int l = 0; l <= k; ++l)
-                L[tri(k, l)] = red[tri(k, l)] + (HASH ? Hs[k * NV + l] : 0.0);
-        __syncwarp();
-        if (!chol_packed<NV>(L, inv)) {
-            status = 2;
-            break;
-        }
-        // ---- predictor ---------------------------------------------------------------------
-        double rh[PV];
+            for (int j = 0; j < NV; ++j) {
+                double v = Lr[j];
 #pragma unroll
-        for (int k = 0; k < PV; ++k) rh[k] = 0.0;
-#pragma unroll
-        for (int j = 0; j < MR; ++j) {
-            if (act >> j & 1u) {
-                const int r = lane + 32 * j;
-                const double t = fma(lam[j], a[j] / s[j], -lam[j]); // (-s.lam + lam rp)/s
-#pragma unroll
-                for (int k = 0; k < NV; ++k) rh[k] = fma(Gs[k * MRP + r], t, rh[k]);
+                for (int k = 0; k < j; ++k) v = fma(-Lr[k], __shfl_sync(kFull, Lr[k], j), v);
+                const double d = __shfl_sync(kFull, v, j);
+                const double dd0 = __shfl_sync(kFull, d0, j);
+                if (!isfinite(d)) bad = true;
+                const double2 pv = chol_pivot(d, dd0);
+                inv[j] = pv.y;
+                Lr[j] = (lane == j) ? pv.x : ((lane > j && lane < NV) ? v * pv.y : 0.0);
             }
+            if (bad) {
+                status = 2;
+                break;
+            }
+            if (lane < NV) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k)
+                    if (k <= lane) red[tri(li, k)] = Lr[k];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < NK; ++k) L[k] = red[k];
+            __syncwarp();
         }
-        warp_reduce_to_smem<PV>(rh, red, NV, lane);
+        // ---- predictor (trip 0) and corrector (trip 1) share one code path -------------------
+        double sig = 0.0, cres = 1.0, alpha = 1.0;
         double dz[NV];
+#pragma unroll 1
+        for (int trip = 0; trip < 2; ++trip) {
+            double rh[PV];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) dz[k] = -rd[k] - red[k];
-        __syncwarp();
-        chol_solve<NV>(L, inv, dz);
-        double amax = 1e300;
+            for (int k = 0; k < PV; ++k) rh[k] = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < MR; ++j) {
+                if (!(act >> j & 1u)) continue;
+                const int r = lane + 32 * j;
+                const double s = sv[r], l = lv[r], rp = av[r];
+                // rc: s.lam (predictor) or s.lam + ds_aff.dl_aff - sigma mu (corrector)
+                double rc = s * l;
+                if (trip) {
+                    rc = rc + bv[r] - sig * mu_mean;
+                    bv[r] = rc;
+                }
+                // rhs = -c (Hz+f) - G'(c lam + t),  t = (lam c rp - rc)/s
+                const double q = fma(cres, l, (l * cres * rp - rc) / s);
 #pragma unroll
-        for (int j = 0; j < MR; ++j) {
-            if (act >> j & 1u) {
+                for (int k = 0; k < NV; ++k) rh[k] = fma(Gs[k * MRP + r], q, rh[k]);
+            }
+            warp_reduce_to_smem<PV>(rh, red, NV, lane);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) dz[k] = -cres * hzf[k] - red[k];
+            __syncwarp();
+            // triangular solves with the replicated factor
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                double v = dz[i];
+#pragma unroll
+                for (int k = 0; k < i; ++k) v = fma(-L[tri(i, k)], dz[k], v);
+                dz[i] = v * inv[i];
+            }
+#pragma unroll
+            for (int i = NV - 1; i >= 0; --i) {
+                double v = dz[i];
+#pragma unroll
+                for (int k = i + 1; k < NV; ++k) v = fma(-L[tri(k, i)], dz[k], v);
+                dz[i] = v * inv[i];
+            }
+            double amax = 1e300;
+#pragma unroll 1
+            for (int j = 0; j < MR; ++j) {
+                if (!(act >> j & 1u)) continue;
                 const int r = lane + 32 * j;
                 double gdz = 0.0;
 #pragma unroll
                 for (int k = 0; k < NV; ++k) gdz = fma(Gs[k * MRP + r], dz[k], gdz);
-                const double ds = -a[j] - gdz;
-                const double dl = -lam[j] - lam[j] * ds / s[j];
-                if (ds < 0.0) amax = fmin(amax, -s[j] / ds);
-                if (dl < 0.0) amax = fmin(amax, -lam[j] / dl);
-                b[j] = ds * dl;
+                const double s = sv[r], l = lv[r];
+                const double rc = trip ? bv[r] : s * l;
+                const double ds = -cres * av[r] - gdz;
+                const double dl = (-rc - l * ds) / s;
+                if (ds < 0.0) amax = fmin(amax, -s / ds);
+                if (dl < 0.0) amax = fmin(amax, -l / dl);
+                if (trip) {
+                    av[r] = ds;
+                    bv[r] = dl;
+                } else {
+                    bv[r] = ds * dl;
+                }
+            }
+            amax = warp_min(amax);
+            if (trip == 0) {
+                const double a_aff = fmin(1.0, amax);
+                sig = (1.0 - a_aff) * (1.0 - a_aff) * (1.0 - a_aff);
+                cres = 1.0 - sig;
+            } else {
+                alpha = fmin(1.0, 0.99 * amax);
             }
         }
-        const double a_aff = fmin(1.0, warp_min(amax));
-        const double sig = (1.0 - a_aff) * (1.0 - a_aff) * (1.0 - a_aff);
-        const double resc = 1.0 - sig;
-        // ---- corrector ---------------------------------------------------------------------
-#pragma unroll
-        for (int k = 0; k < PV; ++k) rh[k] = 0.0;
-#pragma unroll
-        for (int j = 0; j < MR; ++j) {
-            if (act >> j & 1u) {
-                const int r = lane + 32 * j;
-                const double rc = fma(s[j], lam[j], b[j]) - sig * mu_mean;
-                b[j] = rc;
-                const double t = (lam[j] * resc * a[j] - rc) / s[j];
-#pragma unroll
-                for (int k = 0; k < NV; ++k) rh[k] = fma(Gs[k * MRP + r], t, rh[k]);
-            }
-        }
-        warp_reduce_to_smem<PV>(rh, red, NV, lane);
-#pragma unroll
-        for (int k = 0; k < NV; ++k) dz[k] = -resc * rd[k] - red[k];
-        __syncwarp();
-        chol_solve<NV>(L, inv, dz);
-        amax = 1e300;
-#pragma unroll
-        for (int j = 0; j < MR; ++j) {
-            if (act >> j & 1u) {
-                const int r = lane + 32 * j;
-                double gdz = 0.0;
-#pragma unroll
-                for (int k = 0; k < NV; ++k) gdz = fma(Gs[k * MRP + r], dz[k], gdz);
-                const double ds = -resc * a[j] - gdz;
-                const double dl = (-b[j] - lam[j] * ds) / s[j];
-                if (ds < 0.0) amax = fmin(amax, -s[j] / ds);
-                if (dl < 0.0) amax = fmin(amax, -lam[j] / dl);
-                a[j] = ds;
-                b[j] = dl;
-            }
-        }
-        const double alpha = fmin(1.0, 0.99 * warp_min(amax));
+        // ---- step ----------------------------------------------------------------------------
 #pragma unroll
         for (int k = 0; k < NV; ++k) z[k] = fma(alpha, dz[k], z[k]);
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < MR; ++j) {
-            if (act >> j & 1u) {
-                s[j] = fma(alpha, a[j], s[j]);
-                lam[j] = fma(alpha, b[j], lam[j]);
-            }
+            if (!(act >> j & 1u)) continue;
+            const int r = lane + 32 * j;
+            sv[r] = fma(alpha, av[r], sv[r]);
+            lv[r] = fma(alpha, bv[r], lv[r]);
         }
-        rho *= 1.0 - alpha * resc;
+        rho *= 1.0 - alpha * cres;
     }
-    obj_out = obj;
-    iters_out = it;
-    // algorithmic flops (2 per FMA): K build m*NV(NV+1), six mat-vecs 12*m*NV, Cholesky NV^3/3,
-    // two triangular solve pairs 4*NV^2 -- per iteration
-    if (flops_out)
-        *flops_out += (double)it * (mact * (NV * (NV + 1) + 12.0 * NV) + NV * NV * NV / 3.0 + 4.0 * NV * NV);
+    __syncwarp();
+    if (lane < NV) {
+        // static indexing of z by the owning lane
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+            if (lane == k) w[W::oZ + k] = z[k];
+    }
+    if (lane == 0) {
+        w[W::oOut + 0] = obj;
+        w[W::oOut + 1] = (double)it;
+        // algorithmic flops (2 per FMA): K build m*NV(NV+1), five mat-vec passes 10*m*NV,
+        // Cholesky NV^3/3, two triangular solve pairs 4*NV^2 -- per iteration
+        w[W::oOut + 2] = (double)it * (mact * (NV * (NV + 1) + 10.0 * NV) + NV * NV * NV / 3.0 + 4.0 * NV * NV);
+    }
+    __syncwarp();
     return status;
 }
 

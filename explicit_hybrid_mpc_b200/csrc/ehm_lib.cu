@@ -32,7 +32,8 @@ static int find_cfg(int U, int NX, int rows_total)
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 1;   // one problem per CTA-warp; 7 CTAs (28.5 KB each) per SM
+constexpr int kCtasPerSm = 7;
 
 __device__ __forceinline__ long long next_item(DevCounters *cnt, int lane)
 {
@@ -310,7 +311,7 @@ extern "C" int ehm_num_candidates(const ehm_problem *p) { return p ? p->tb.ncand
 static int grid_for(const ehm_problem *p, long long items)
 {
     const long long ctas = (items + kWarpsPerCta - 1) / kWarpsPerCta;
-    const long long cap = (long long)p->sm_count * 2;  // 2 CTAs (8 warps) resident per SM
+    const long long cap = (long long)p->sm_count * kCtasPerSm;
     return (int)std::max(1ll, std::min(ctas, cap));
 }
 
@@ -410,6 +411,12 @@ struct ehm_partition {
     Ctl hctl{};
     std::vector<void *> allocs;
     int n = 0, nu = 0;
+    ehm_partition_opts opts{};
+    int ecc_q0 = 0;                 // ECC queue cursor
+    DevCounters c0{};               // counters at creation
+    double sms[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sbytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double device_ms = 0;
+    int64_t launches = 0, waves = 0;
     template <typename T>
     int alloc(T **p, size_t count)
     {
@@ -426,11 +433,29 @@ struct ehm_partition {
 
 namespace {
 
+void fill_stats(ehm_partition *t, ehm_partition_stats *stats)
+{
+    if (!stats) return;
+    DevCounters c1;
+    cudaMemcpy(&c1, t->pb->dcnt, sizeof c1, cudaMemcpyDeviceToHost);
+    const Ctl &h = t->hctl;
+    const DevCounters &c0 = t->c0;
+    stats->nnodes = h.nnodes; stats->nleaves = h.nleaves;
+    stats->nsolves = (int64_t)(c1.solves - c0.solves); stats->niters = (int64_t)(c1.iters - c0.iters);
+    stats->nfail = (int64_t)(c1.fails - c0.fails); stats->nwaves = t->waves; stats->nlaunches = t->launches;
+    stats->open_left = h.ftop + (h.necc_next - t->ecc_q0); stats->max_depth = h.max_depth;
+    stats->device_ms = t->device_ms;
+    for (int k = 0; k < 8; ++k) { stats->stage_ms[k] = t->sms[k]; stats->stage_bytes[k] = t->sbytes[k]; stats->stage_flops[k] = 0; }
+    stats->stage_flops[1] = c1.flops[1] - c0.flops[1]; stats->stage_flops[3] = c1.flops[2] - c0.flops[2];
+    stats->stage_flops[5] = c1.flops[3] - c0.flops[3]; stats->stage_flops[7] = c1.flops[4] - c0.flops[4];
+}
+
 template <int U, int NX, int MR>
-int run_partition_t(ehm_partition *t, int nroots, const ehm_partition_opts &o, ehm_partition_stats *stats)
+int advance_t(ehm_partition *t, int64_t max_waves)
 {
     ehm_problem *p = t->pb;
     const DevTables &tb = p->tb;
+    const ehm_partition_opts &o = t->opts;
     const int ncand = tb.ncand;
     const size_t smem = (size_t)kWarpsPerCta * WarpWs<U, NX, MR>::kDoubles * sizeof(double);
     auto kref = k_lcss_ref<U, NX, MR>;
@@ -441,45 +466,39 @@ int run_partition_t(ehm_partition *t, int nroots, const ehm_partition_opts &o, e
     if ((rc = set_smem(kref, smem)) || (rc = set_smem(keval, smem)) || (rc = set_smem(kpts, smem)) ||
         (rc = set_smem(kecc, smem)))
         return rc;
-    const int gsolve = p->sm_count * 2, tsolve = 32 * kWarpsPerCta;
+    const int gsolve = p->sm_count * kCtasPerSm, tsolve = 32 * kWarpsPerCta;
     const int gaux = p->sm_count * 4, taux = 256;
     cudaStream_t st = 0;
-    cudaEvent_t ev0, ev1;
+    cudaEvent_t ev0, ev1, sev[8];
     EHM_CUDA(cudaEventCreate(&ev0));
     EHM_CUDA(cudaEventCreate(&ev1));
-    DevCounters c0;
-    EHM_CUDA(cudaMemcpy(&c0, p->dcnt, sizeof c0, cudaMemcpyDeviceToHost));
+    for (auto &e : sev) EHM_CUDA(cudaEventCreate(&e));
     EHM_CUDA(cudaEventRecord(ev0, st));
     int64_t launches = 0, waves = 0;
     Ctl &h = t->hctl;
     // ---- ECC phase: roots (and their ECC descendants) -> L-CSS entries on the frontier ----
-    int q0 = 0;
-    while (q0 < h.necc_next && h.error == 0) {
+    while (t->ecc_q0 < h.necc_next && h.error == 0 && (max_waves <= 0 || waves < max_waves)) {
+        const int q0 = t->ecc_q0;
         const int ne = std::min(kEccWave, h.necc_next - q0);
+        EHM_CUDA(cudaEventRecord(sev[0], st));
         k_reset_cursors<<<1, 32, 0, st>>>(t->dctl);
         kecc<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->eb, q0, ne, 0, t->dctl, p->dcnt);
         k_ecc_pick<NX><<<(ne * 32 + 127) / 128, 128, 0, st>>>(tb, t->eb, ne, t->dctl);
         kecc<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->eb, q0, ne, 1, t->dctl, p->dcnt);
         k_ecc_final<NX><<<(ne * 32 + 127) / 128, 128, 0, st>>>(tb, t->ns, t->fr, t->eb, q0, ne, t->dctl);
+        EHM_CUDA(cudaEventRecord(sev[1], st));
         launches += 5;
         EHM_CUDA(cudaMemcpyAsync(&h, t->dctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
         EHM_CUDA(cudaStreamSynchronize(st));
-        q0 += ne;
+        float ems = 0;
+        cudaEventElapsedTime(&ems, sev[0], sev[1]);
+        t->sms[7] += ems;
+        t->ecc_q0 += ne;
         ++waves;
-        if (o.verbose) fprintf(stderr, "[ehm] ecc wave: queue %d/%d frontier %d nodes %d\n", q0, h.necc_next, h.ftop, h.nnodes);
+        if (o.verbose) fprintf(stderr, "[ehm] ecc wave: queue %d/%d frontier %d nodes %d\n", t->ecc_q0, h.necc_next, h.ftop, h.nnodes);
     }
     // ---- L-CSS phase ------------------------------------------------------------------------
-    cudaEvent_t sev[8];
-    for (auto &e : sev) EHM_CUDA(cudaEventCreate(&e));
-    double sms[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sbytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    {
-        float ems = 0;
-        EHM_CUDA(cudaEventRecord(sev[0], st));
-        EHM_CUDA(cudaEventSynchronize(sev[0]));
-        cudaEventElapsedTime(&ems, ev0, sev[0]);
-        sms[7] = ems;
-    }
-    while (h.ftop > 0 && h.error == 0) {
+    while (h.ftop > 0 && h.error == 0 && (max_waves <= 0 || waves < max_waves)) {
         if (o.node_budget > 0 && h.nnodes >= o.node_budget) break;
         const int W = std::min(t->wv.W, h.ftop);
         const int base = h.ftop - W;
@@ -505,39 +524,31 @@ int run_partition_t(ehm_partition *t, int nroots, const ehm_partition_opts &o, e
         for (int k = 0; k < 7; ++k) {
             float ems = 0;
             cudaEventElapsedTime(&ems, sev[k], sev[k + 1]);
-            sms[k] += ems;
+            t->sms[k] += ems;
         }
         // algorithmic HBM bytes of the streaming stages: pop moves W bound rows (read+write),
         // items reads them and writes tval(8)+titem(4), final reads one row and writes one
         // row per pushed entry
-        sbytes[0] += 2.0 * W * ncand * 4.0;
-        sbytes[2] += (double)W * ncand * 16.0;
-        sbytes[6] += (double)(h.ftop - ftop_before) * ncand * 8.0;
+        t->sbytes[0] += 2.0 * W * ncand * 4.0;
+        t->sbytes[2] += (double)W * ncand * 16.0;
+        t->sbytes[6] += (double)(h.ftop - ftop_before) * ncand * 8.0;
         ++waves;
         if (o.verbose)
             fprintf(stderr, "[ehm] wave %lld: popped %d items %d pitems %d -> frontier %d nodes %d leaves %d\n",
-                    (long long)waves, W, h.nitems, h.npitems, h.ftop, h.nnodes, h.nleaves);
+                    (long long)(t->waves + waves), W, h.nitems, h.npitems, h.ftop, h.nnodes, h.nleaves);
     }
-    for (auto &e : sev) cudaEventDestroy(e);
     EHM_CUDA(cudaEventRecord(ev1, st));
     EHM_CUDA(cudaEventSynchronize(ev1));
     EHM_CUDA(cudaGetLastError());
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
+    for (auto &e : sev) cudaEventDestroy(e);
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
-    DevCounters c1;
-    EHM_CUDA(cudaMemcpy(&c1, p->dcnt, sizeof c1, cudaMemcpyDeviceToHost));
+    t->device_ms += ms;
+    t->launches += launches;
+    t->waves += waves;
     g_launches += launches;
-    if (stats) {
-        stats->nnodes = h.nnodes; stats->nleaves = h.nleaves;
-        stats->nsolves = (int64_t)(c1.solves - c0.solves); stats->niters = (int64_t)(c1.iters - c0.iters);
-        stats->nfail = (int64_t)(c1.fails - c0.fails); stats->nwaves = waves; stats->nlaunches = launches;
-        stats->open_left = h.ftop; stats->max_depth = h.max_depth; stats->device_ms = ms;
-        for (int k = 0; k < 8; ++k) { stats->stage_ms[k] = sms[k]; stats->stage_bytes[k] = sbytes[k]; stats->stage_flops[k] = 0; }
-        stats->stage_flops[1] = c1.flops[1] - c0.flops[1]; stats->stage_flops[3] = c1.flops[2] - c0.flops[2];
-        stats->stage_flops[5] = c1.flops[3] - c0.flops[3]; stats->stage_flops[7] = c1.flops[4] - c0.flops[4];
-    }
     if (h.error == EHM_EINFEASIBLE) return fail(EHM_EINFEASIBLE, "STOP, Theta contains infeasible regions");
     if (h.error == EHM_ECAPACITY) return fail(EHM_ECAPACITY, "node store or frontier capacity exhausted");
     if (h.error == EHM_ENUMERIC) return fail(EHM_ENUMERIC, "midpoint vertex problem infeasible");
@@ -546,11 +557,10 @@ int run_partition_t(ehm_partition *t, int nroots, const ehm_partition_opts &o, e
 
 }  // namespace
 
-extern "C" int ehm_partition_run(ehm_problem *p, int nroots, const double *roots,
-                                 const ehm_partition_opts *opts, ehm_partition **out,
-                                 ehm_partition_stats *stats)
+extern "C" int ehm_partition_create(ehm_problem *p, int nroots, const double *roots,
+                                    const ehm_partition_opts *opts, ehm_partition **out)
 {
-    if (!p || nroots <= 0 || !roots || !out) return fail(EHM_EINVAL, "bad argument");
+    if (!p || nroots < 0 || (nroots > 0 && !roots) || !out) return fail(EHM_EINVAL, "bad argument");
     *out = nullptr;
     ehm_partition_opts o{};
     if (opts) o = *opts;
@@ -561,7 +571,7 @@ extern "C" int ehm_partition_run(ehm_problem *p, int nroots, const double *roots
     const int64_t fcap = o.max_frontier > 0 ? o.max_frontier : std::max<int64_t>(65536, 16 * (int64_t)W);
     if (maxn > 0x7ffffff0ll || fcap > 0x7ffffff0ll || nroots > maxn) return fail(EHM_EINVAL, "capacity too large");
     ehm_partition *t = new ehm_partition();
-    t->pb = p; t->n = n; t->nu = nu;
+    t->pb = p; t->n = n; t->nu = nu; t->opts = o;
     int rc = EHM_OK;
     auto A = [&](int r) { if (rc == EHM_OK) rc = r; };
     NodeStore &ns = t->ns;
@@ -569,7 +579,7 @@ extern "C" int ehm_partition_run(ehm_problem *p, int nroots, const double *roots
     A(t->alloc(&ns.verts, (size_t)maxn * (n + 1) * n)); A(t->alloc(&ns.vcost, (size_t)maxn * (n + 1)));
     A(t->alloc(&ns.vinput, (size_t)maxn * (n + 1) * nu)); A(t->alloc(&ns.cand, maxn));
     A(t->alloc(&ns.left, maxn)); A(t->alloc(&ns.right, maxn)); A(t->alloc(&ns.root_id, maxn));
-    A(t->alloc(&ns.depth, maxn)); A(t->alloc(&ns.closed, maxn));
+    A(t->alloc(&ns.depth, maxn)); A(t->alloc(&ns.closed, maxn)); A(t->alloc(&ns.origin, (size_t)2 * maxn));
     Frontier &fr = t->fr;
     fr.cap = (int)fcap;
     A(t->alloc(&fr.node, fcap)); A(t->alloc(&fr.skip, fcap)); A(t->alloc(&fr.lb, (size_t)fcap * ncand));
@@ -593,34 +603,175 @@ extern "C" int ehm_partition_run(ehm_problem *p, int nroots, const double *roots
     if (rc != EHM_OK) { delete t; return rc; }
     // root nodes
     {
-        std::vector<int> iz(nroots, -1), id(nroots), zero(nroots, 0);
+        std::vector<int> iz(std::max(nroots, 1), -1), id(std::max(nroots, 1)), zero(std::max(nroots, 1), 0);
+        std::vector<int> org((size_t)2 * std::max(nroots, 1), -1);
         for (int i = 0; i < nroots; ++i) id[i] = i;
-        std::vector<unsigned char> cz(nroots, 0);
-        cudaError_t e = cudaMemcpy(ns.verts, roots, (size_t)nroots * (n + 1) * n * sizeof(double), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemset(ns.vcost, 0, (size_t)nroots * (n + 1) * sizeof(double));
-        if (e == cudaSuccess) e = cudaMemset(ns.vinput, 0, (size_t)nroots * (n + 1) * nu * sizeof(double));
-        if (e == cudaSuccess) e = cudaMemcpy(ns.cand, iz.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(ns.left, iz.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(ns.right, iz.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(ns.root_id, id.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(ns.depth, zero.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(ns.closed, cz.data(), nroots, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(eb.queue, id.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+        std::vector<unsigned char> cz(std::max(nroots, 1), 0);
+        cudaError_t e = cudaSuccess;
+        if (nroots > 0) {
+            e = cudaMemcpy(ns.verts, roots, (size_t)nroots * (n + 1) * n * sizeof(double), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemset(ns.vcost, 0, (size_t)nroots * (n + 1) * sizeof(double));
+            if (e == cudaSuccess) e = cudaMemset(ns.vinput, 0, (size_t)nroots * (n + 1) * nu * sizeof(double));
+            if (e == cudaSuccess) e = cudaMemcpy(ns.cand, iz.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(ns.left, iz.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(ns.right, iz.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(ns.root_id, id.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(ns.depth, zero.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(ns.closed, cz.data(), nroots, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(ns.origin, org.data(), (size_t)2 * nroots * sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(eb.queue, id.data(), nroots * sizeof(int), cudaMemcpyHostToDevice);
+        }
         memset(&t->hctl, 0, sizeof(Ctl));
         t->hctl.nnodes = nroots;
         t->hctl.necc_next = nroots;
         if (e == cudaSuccess) e = cudaMemcpy(t->dctl, &t->hctl, sizeof(Ctl), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(&t->c0, p->dcnt, sizeof(DevCounters), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { delete t; return fail(EHM_ECUDA, std::string("root upload: ") + cudaGetErrorString(e)); }
     }
-    switch (p->cfg) {
+    *out = t;
+    return EHM_OK;
+}
+
+extern "C" int ehm_partition_set_root_ids(ehm_partition *t, int nroots, const int32_t *ids)
+{
+    if (!t || nroots < 0 || nroots > t->hctl.nnodes || (nroots > 0 && !ids)) return fail(EHM_EINVAL, "bad argument");
+    if (nroots == 0) return EHM_OK;
+    EHM_CUDA(cudaMemcpy(t->ns.root_id, ids, (size_t)nroots * sizeof(int), cudaMemcpyHostToDevice));
+    return EHM_OK;
+}
+
+extern "C" int ehm_partition_advance(ehm_partition *t, int64_t max_waves, ehm_partition_stats *stats)
+{
+    if (!t) return fail(EHM_EINVAL, "null partition");
+    int rc;
+    switch (t->pb->cfg) {
 #define X(ID, UU, NN, MM) \
-    case ID: rc = run_partition_t<UU, NN, MM>(t, nroots, o, stats); break;
+    case ID: rc = advance_t<UU, NN, MM>(t, max_waves); break;
         EHM_FOR_EACH_CFG(X)
 #undef X
     default: rc = fail(EHM_EINVAL, "no kernel for this problem shape");
     }
-    *out = t;  // returned even on error so the partial tree can be inspected
+    fill_stats(t, stats);
     return rc;
+}
+
+extern "C" int ehm_partition_run(ehm_problem *p, int nroots, const double *roots,
+                                 const ehm_partition_opts *opts, ehm_partition **out,
+                                 ehm_partition_stats *stats)
+{
+    if (!out || nroots <= 0) return fail(EHM_EINVAL, "bad argument");
+    int rc = ehm_partition_create(p, nroots, roots, opts, out);
+    if (rc != EHM_OK) return rc;
+    return ehm_partition_advance(*out, 0, stats);  // *out stays valid on error (partial tree)
+}
+
+// ---- frontier exchange between ranks (multi-GPU rebalance) --------------------------------
+// Records: meta int32[k][6] = {origin node id, cand, depth, root_id, skip, 0},
+//          geom f64[k][(n+1)n + (n+1) + (n+1)nu], lb f32[k][ncand].
+__global__ void k_export(NodeStore ns, Frontier fr, int ftop, int k, int n, int nu, int ncand,
+                         int *meta, double *geom, float *lb)
+{
+    // exported entries are the k OLDEST (bottom of the stack: largest sub-trees); the holes are
+    // refilled with the youngest entries so that the stack stays dense
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int ng = (n + 1) * n + (n + 1) + (n + 1) * nu;
+    for (int e = gw; e < k; e += nw) {
+        const int nd = fr.node[e];
+        for (int c = lane; c < ncand; c += 32) lb[(size_t)e * ncand + c] = fr.lb[(size_t)e * ncand + c];
+        for (int q = lane; q < ng; q += 32) {
+            double v;
+            if (q < (n + 1) * n) v = ns.verts[(size_t)nd * (n + 1) * n + q];
+            else if (q < (n + 1) * n + (n + 1)) v = ns.vcost[(size_t)nd * (n + 1) + q - (n + 1) * n];
+            else v = ns.vinput[(size_t)nd * (n + 1) * nu + q - (n + 1) * n - (n + 1)];
+            geom[(size_t)e * ng + q] = v;
+        }
+        if (lane == 0) {
+            meta[e * 6 + 0] = nd; meta[e * 6 + 1] = ns.cand[nd]; meta[e * 6 + 2] = ns.depth[nd];
+            meta[e * 6 + 3] = ns.root_id[nd]; meta[e * 6 + 4] = fr.skip[e]; meta[e * 6 + 5] = 0;
+            ns.closed[nd] = 2;  // exported: continued on another rank
+        }
+    }
+}
+
+__global__ void k_refill(Frontier fr, int ftop, int k, int ncand)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int e = gw; e < k; e += nw) {
+        const int src = ftop - 1 - e;
+        if (src < k) continue;  // that slot is itself being exported
+        for (int c = lane; c < ncand; c += 32) fr.lb[(size_t)e * ncand + c] = fr.lb[(size_t)src * ncand + c];
+        if (lane == 0) {
+            fr.node[e] = fr.node[src];
+            fr.skip[e] = fr.skip[src];
+        }
+    }
+}
+
+__global__ void k_import(NodeStore ns, Frontier fr, int node0, int pos0, int k, int n, int nu, int ncand,
+                         const int *meta, const double *geom, const float *lb, const int *origin_rank)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int ng = (n + 1) * n + (n + 1) + (n + 1) * nu;
+    for (int e = gw; e < k; e += nw) {
+        const int nd = node0 + e, pos = pos0 + e;
+        for (int c = lane; c < ncand; c += 32) fr.lb[(size_t)pos * ncand + c] = lb[(size_t)e * ncand + c];
+        for (int q = lane; q < ng; q += 32) {
+            const double v = geom[(size_t)e * ng + q];
+            if (q < (n + 1) * n) ns.verts[(size_t)nd * (n + 1) * n + q] = v;
+            else if (q < (n + 1) * n + (n + 1)) ns.vcost[(size_t)nd * (n + 1) + q - (n + 1) * n] = v;
+            else ns.vinput[(size_t)nd * (n + 1) * nu + q - (n + 1) * n - (n + 1)] = v;
+        }
+        if (lane == 0) {
+            ns.cand[nd] = meta[e * 6 + 1]; ns.depth[nd] = meta[e * 6 + 2]; ns.root_id[nd] = meta[e * 6 + 3];
+            ns.left[nd] = -1; ns.right[nd] = -1; ns.closed[nd] = 0;
+            ns.origin[2 * nd] = origin_rank[e]; ns.origin[2 * nd + 1] = meta[e * 6 + 0];
+            fr.node[pos] = nd; fr.skip[pos] = meta[e * 6 + 4];
+        }
+    }
+}
+
+extern "C" int ehm_partition_export(ehm_partition *t, int k, int32_t *d_meta, double *d_geom, float *d_lb)
+{
+    if (!t || k < 0 || (k > 0 && (!d_meta || !d_geom || !d_lb))) return fail(EHM_EINVAL, "bad argument");
+    Ctl &h = t->hctl;
+    if (k > h.ftop) return fail(EHM_EINVAL, "export count exceeds frontier size");
+    if (k == 0) return EHM_OK;
+    const int ncand = t->pb->tb.ncand;
+    k_export<<<t->pb->sm_count * 4, 256>>>(t->ns, t->fr, h.ftop, k, t->n, t->nu, ncand, d_meta, d_geom, d_lb);
+    k_refill<<<t->pb->sm_count * 4, 256>>>(t->fr, h.ftop, k, ncand);
+    g_launches += 2;
+    h.ftop -= k;
+    EHM_CUDA(cudaMemcpy(&t->dctl->ftop, &h.ftop, sizeof(int), cudaMemcpyHostToDevice));
+    EHM_CUDA(cudaGetLastError());
+    return EHM_OK;
+}
+
+extern "C" int ehm_partition_import(ehm_partition *t, int k, const int32_t *d_meta, const double *d_geom,
+                                    const float *d_lb, const int32_t *d_origin_rank)
+{
+    if (!t || k < 0 || (k > 0 && (!d_meta || !d_geom || !d_lb || !d_origin_rank))) return fail(EHM_EINVAL, "bad argument");
+    if (k == 0) return EHM_OK;
+    Ctl &h = t->hctl;
+    if (h.nnodes + k > t->ns.cap || h.ftop + k > t->fr.cap) return fail(EHM_ECAPACITY, "import exceeds capacity");
+    k_import<<<t->pb->sm_count * 4, 256>>>(t->ns, t->fr, h.nnodes, h.ftop, k, t->n, t->nu, t->pb->tb.ncand, d_meta,
+                                            d_geom, d_lb, d_origin_rank);
+    g_launches += 1;
+    h.nnodes += k;
+    h.ftop += k;
+    EHM_CUDA(cudaMemcpy(&t->dctl->ftop, &h.ftop, sizeof(int), cudaMemcpyHostToDevice));
+    EHM_CUDA(cudaMemcpy(&t->dctl->nnodes, &h.nnodes, sizeof(int), cudaMemcpyHostToDevice));
+    EHM_CUDA(cudaGetLastError());
+    return EHM_OK;
+}
+
+extern "C" int ehm_partition_fetch_origin(ehm_partition *t, int32_t *origin)
+{
+    if (!t || !origin) return fail(EHM_EINVAL, "bad argument");
+    EHM_CUDA(cudaMemcpy(origin, t->ns.origin, (size_t)2 * t->hctl.nnodes * sizeof(int), cudaMemcpyDeviceToHost));
+    return EHM_OK;
 }
 
 extern "C" int ehm_partition_fetch(ehm_partition *t, int32_t *left, int32_t *right, int32_t *root_id,

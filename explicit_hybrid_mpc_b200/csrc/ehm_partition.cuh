@@ -48,7 +48,8 @@ struct NodeStore {
     int cap;
     double *verts, *vcost, *vinput;
     int *cand, *left, *right, *root_id, *depth;
-    unsigned char *closed;
+    unsigned char *closed;   // 0 open / interior, 1 eps-suboptimal leaf, 2 exported to another rank
+    int *origin;             // [cap][2] (rank, node) this node continues, -1 = local
 };
 
 struct Frontier {
@@ -513,6 +514,8 @@ __global__ void k_lcss_final(DevTables tb, NodeStore ns, Frontier fr, WaveBuf wv
                 ns.root_id[ch] = ns.root_id[nd];
                 ns.depth[ch] = dep;
                 ns.closed[ch] = 0;
+                ns.origin[2 * ch] = -1;
+                ns.origin[2 * ch + 1] = -1;
                 fr.node[pos + side] = ch;
                 fr.skip[pos + side] = 0;
             }
@@ -680,6 +683,8 @@ __global__ void k_ecc_final(DevTables tb, NodeStore ns, Frontier fr, EccBuf eb, 
         ns.root_id[ch] = ns.root_id[nd];
         ns.depth[ch] = dep;
         ns.closed[ch] = 0;
+        ns.origin[2 * ch] = -1;
+        ns.origin[2 * ch + 1] = -1;
         eb.queue[qp + side] = ch;
     }
 }

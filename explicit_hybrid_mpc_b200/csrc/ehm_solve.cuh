@@ -7,6 +7,12 @@
 //   tqp     : eps-suboptimality epigraph problem  variables [u;beta;tau] (U+NX+1)  (:88-97)
 //   minv    : min over simplex of V*_c            variables [u;beta]     (U+NX)    (:75-79)
 //
+// Every problem class runs through ONE instantiation of ipm_solve (point problems NV=U+1,
+// simplex problems NV=U+NX+1): the phase-1 variable sigma, the epigraph variable tau and --
+// where a problem has one variable less -- an inert dummy column (zero coefficients, zero
+// cost; its Cholesky pivot is frozen by the guard) share the last column.  That keeps the hot
+// code of a kernel inside the instruction cache.
+//
 // Candidate tables live in global memory (L2 resident: 60 MB for the pendulum), column-major
 // with the row index fastest so that a warp's load of one column is one coalesced 256 B
 // segment per 32 rows.
@@ -26,24 +32,27 @@ struct DevTables {
     double eps_a, eps_r;
 };
 
-// Shared-memory workspace of one warp (all sizes in doubles, compile-time).
+// Shared-memory workspace of one warp: the solver block of the widest problem; the assembly
+// scratch (cost transform, simplex geometry) aliases the per-row state vectors, which are
+// only live inside ipm_solve.
 template <int U, int NX, int MR>
 struct WarpWs {
     static constexpr int NVS = U + NX + 1;
+    static constexpr int NVP = U + 1;
+    using WS = IpmWs<NVS, MR>;
+    using WP = IpmWs<NVP, MR>;
     static constexpr int MRP = 32 * MR;
     static constexpr int Y = U + NX + 1;
-    static constexpr int oG = 0;
-    static constexpr int oH = oG + NVS * MRP;    // hs
-    static constexpr int oHs = oH + MRP;         // Hessian NVS*NVS
-    static constexpr int oF = oHs + NVS * NVS;   // f (padded 16)
-    static constexpr int oRed = oF + 16;         // 64
-    static constexpr int oM = oRed + 64;         // candidate M (Y*Y)
-    static constexpr int oT = oM + Y * Y;        // T (Y*Y)
-    static constexpr int oMT = oT + Y * Y;       // M*T (Y*Y)
-    static constexpr int oR = oMT + Y * Y;       // simplex vertices (NX+1)*NX
-    static constexpr int oE = oR + (NX + 1) * NX;  // E NX*NX
-    static constexpr int oV = oE + NX * NX;      // Vr (NX+1), padded 16
-    static constexpr int kDoubles = oV + 16;
+    static constexpr int kDoubles = WS::kDoubles;
+    // scratch inside the simplex block's s/lam/a/b region (4*MRP doubles)
+    static constexpr int oM = WS::oS;               // candidate M, later Mp (Y*Y)
+    static constexpr int oT = oM + Y * Y;           // T (Y*Y)
+    static constexpr int oMT = oT + Y * Y;          // M*T (Y*Y)
+    static constexpr int oR = oMT + Y * Y;          // simplex vertices (NX+1)*NX
+    static constexpr int oE = oR + (NX + 1) * NX;   // E NX*NX
+    static constexpr int oV = oE + NX * NX;         // Vr (NX+1), padded 16
+    static_assert(oV + 16 <= WS::oHs, "assembly scratch must fit the row-state region");
+    static_assert(WP::kDoubles <= WS::kDoubles, "point block must fit the simplex block");
 };
 
 struct SolveOut {
@@ -54,18 +63,29 @@ struct SolveOut {
     double flops; // algorithmic flops spent (see ipm_solve)
 };
 
+template <int NV, int MR>
+__device__ __forceinline__ int run_ipm(double *ws, unsigned act, int lane, SolveOut &out, double &obj)
+{
+    using W = IpmWs<NV, MR>;
+    const int st = ipm_solve<NV, MR>(ws, act, lane);
+    obj = ws[W::oOut + 0];
+    out.iters += (int)ws[W::oOut + 1];
+    out.flops += ws[W::oOut + 2];
+    out.nsolves++;
+    __syncwarp();
+    return st;
+}
+
 // ---------------------------------------------------------------------------------------
 // P_theta_delta at one theta for candidate c.   u0 (nu values) written to u0_out by lane 0.
-// skip_phase1: the caller knows the point is strictly feasible (midpoints, vertices).
 // ---------------------------------------------------------------------------------------
 template <int U, int NX, int MR>
 __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__restrict__ theta,
                                 double *ws, double *u0_out, int lane)
 {
-    using W = WarpWs<U, NX, MR>;
-    constexpr int MRP = W::MRP;
-    double *Gs = ws + W::oG, *hs = ws + W::oH, *Hs = ws + W::oHs, *fs = ws + W::oF,
-           *red = ws + W::oRed;
+    using W = typename WarpWs<U, NX, MR>::WP;
+    constexpr int MRP = W::MRP, NV = U + 1;
+    double *Gs = ws + W::oG, *hs = ws + W::oH, *Hs = ws + W::oHs, *fs = ws + W::oF, *zs = ws + W::oZ;
     SolveOut out{0, 0.0, 0, 0, 0.0};
     const int MP = tb.MP, m = tb.m, Y = tb.Y;
     const double *Gc = tb.G + (size_t)c * U * MP, *Sc = tb.S + (size_t)c * NX * MP,
@@ -76,7 +96,7 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
     unsigned act = 0;
     bool viol = false;
     double s0 = 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < MR; ++j) {
         const int r = lane + 32 * j;
         if (r < m) {
@@ -106,31 +126,24 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
     }
     if (__any_sync(kFull, viol)) return out;
     s0 = warp_max(s0);
-    __syncwarp();
     // ---- phase 1: min sigma s.t. G u - sigma <= h --------------------------------------
-    {
-        if (lane < 16) fs[lane] = (lane == U) ? 1.0 : 0.0;
-        __syncwarp();
-        double z[U + 1];
-#pragma unroll
-        for (int k = 0; k < U; ++k) z[k] = 0.0;
-        z[U] = s0 + 1.0;
-        double obj;
-        int it;
-        const int st = ipm_solve<U + 1, MR, false>(Gs, hs, act, Hs, fs, red, z, obj, it, lane, &out.flops);
-        out.iters += it;
-        out.nsolves++;
-        if (st != 0) {
-            out.status = -1;
-            return out;
-        }
-        if (!(obj <= -EHM_TAU_INT)) return out;
+    for (int e = lane; e < NV * NV; e += 32) Hs[e] = 0.0;
+    if (lane < 16) {
+        fs[lane] = (lane == U) ? 1.0 : 0.0;
+        zs[lane] = (lane == U) ? s0 + 1.0 : 0.0;
     }
-    // ---- phase 2: the QP ------------------------------------------------------------------
+    __syncwarp();
+    double obj;
+    int st = run_ipm<NV, MR>(ws, act, lane, out, obj);
+    if (st != 0) {
+        out.status = -1;
+        return out;
+    }
+    if (!(obj <= -EHM_TAU_INT)) return out;
+    // ---- phase 2: the QP (last column becomes an inert dummy) ------------------------------
     const double *Mc = tb.M + (size_t)c * Y * Y;
     double cs = 1.0, cst = 0.0;
     {
-        // H = 2 M_uu, f = 2 (M_u,theta theta + M_u,1)
         double fv = 0.0, hd = 0.0;
         if (lane < U) {
             fv = Mc[lane * Y + Y - 1];
@@ -140,8 +153,17 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
             hd = 2.0 * Mc[lane * Y + lane];
         }
         cs = fmax(1.0, warp_max(fmax(fabs(fv), fabs(hd))));
-        if (lane < U) fs[lane] = fv / cs;
-        for (int e = lane; e < U * U; e += 32) Hs[e] = 2.0 * Mc[(e / U) * Y + (e % U)] / cs;
+        if (lane < 16) {
+            fs[lane] = (lane < U) ? fv / cs : 0.0;
+            zs[lane] = 0.0;
+        }
+        for (int e = lane; e < NV * NV; e += 32) {
+            const int a = e / NV, b = e % NV;
+            Hs[e] = (a < U && b < U) ? 2.0 * Mc[a * Y + b] / cs : 0.0;
+        }
+#pragma unroll 1
+        for (int j = 0; j < MR; ++j)
+            if (act >> j & 1u) Gs[U * MRP + lane + 32 * j] = 0.0;
         cst = Mc[(Y - 1) * Y + Y - 1];
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
@@ -151,43 +173,34 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
         }
         __syncwarp();
     }
-    double z[U];
-#pragma unroll
-    for (int k = 0; k < U; ++k) z[k] = 0.0;
-    double obj;
-    int it;
-    const int st = ipm_solve<U, MR, true>(Gs, hs, act, Hs, fs, red, z, obj, it, lane, &out.flops);
-    out.iters += it;
-    out.nsolves++;
+    st = run_ipm<NV, MR>(ws, act, lane, out, obj);
     if (st != 0) {
         out.status = -1;
         return out;
     }
     out.status = 1;
     out.val = cs * obj + cst;
-    if (u0_out != nullptr && lane == 0) {
-#pragma unroll
-        for (int k = 0; k < U; ++k)
-            if (k < tb.nu) u0_out[k] = z[k];
-    }
+    if (u0_out != nullptr && lane < tb.nu && lane < U) u0_out[lane] = zs[lane];
+    __syncwarp();
     return out;
 }
 
 // ---------------------------------------------------------------------------------------
 // Simplex problems.  Rv: (NX+1)*NX vertices (global), Vr: NX+1 vertex costs (global, TQP).
 // mode: EHM_SX_ALIVE / EHM_SX_TQP / EHM_SX_MINV;  phase1: run the alive test first.
-// sol (optional, global, NX+1 doubles): [beta*, V*] written by lane 0 for TQP / MINV.
+// sol (optional, global, NX+1 doubles): [beta*, V*] written for TQP / MINV.
 // ---------------------------------------------------------------------------------------
 template <int U, int NX, int MR>
 __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__restrict__ Rv,
                                   const double *__restrict__ Vr, int mode, bool phase1,
                                   double *ws, double *sol, int lane)
 {
-    using W = WarpWs<U, NX, MR>;
-    constexpr int MRP = W::MRP, NB = U + NX, NVS = U + NX + 1, Y = W::Y;
-    double *Gs = ws + W::oG, *hs = ws + W::oH, *Hs = ws + W::oHs, *fs = ws + W::oF,
-           *red = ws + W::oRed, *Ms = ws + W::oM, *Ts = ws + W::oT, *MTs = ws + W::oMT,
-           *Rs = ws + W::oR, *Es = ws + W::oE, *Vs = ws + W::oV;
+    using WW = WarpWs<U, NX, MR>;
+    using W = typename WW::WS;
+    constexpr int MRP = W::MRP, NB = U + NX, NVS = U + NX + 1, Y = WW::Y;
+    double *Gs = ws + W::oG, *hs = ws + W::oH, *Hs = ws + W::oHs, *fs = ws + W::oF, *zs = ws + W::oZ,
+           *Ms = ws + WW::oM, *Ts = ws + WW::oT, *MTs = ws + WW::oMT, *Rs = ws + WW::oR,
+           *Es = ws + WW::oE, *Vs = ws + WW::oV;
     SolveOut out{0, 0.0, 0, 0, 0.0};
     const int MP = tb.MP, m = tb.m;
     const double *Gc = tb.G + (size_t)c * U * MP, *Sc = tb.S + (size_t)c * NX * MP,
@@ -207,10 +220,10 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         for (int i = 0; i <= NX; ++i) cs = fmax(cs, fabs(Vs[i]));
     }
     const bool tau = (mode == EHM_SX_TQP);
-    unsigned act = 0;
+    unsigned act = 0, tau_bits = 0;
     bool viol = false;
     double s0 = 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < MR; ++j) {
         const int r = lane + 32 * j;
         double co[NB], hv = 0.0, rho = 1.0, last = 0.0;
@@ -260,6 +273,7 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
             hv = (r == m + NX + 1) ? Vs[0] - tb.eps_a : Vs[0] * k2;
             rho = n1;
             have = true;
+            tau_bits |= 1u << j;
         }
         if (have) {
             double nrm = fabs(last);
@@ -272,45 +286,34 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
                 const double inv = 1.0 / nrm;
 #pragma unroll
                 for (int k = 0; k < NB; ++k) Gs[k * MRP + r] = co[k] * inv;
-                Gs[NB * MRP + r] = last * inv;  // tau column (overwritten with -1 for sigma)
+                Gs[NB * MRP + r] = last * inv;  // tau column
                 hs[r] = hv * inv;
                 // rows carrying tau do not exist in the phase-1 problem
-                if (!(tau && r > m + NX)) s0 = fmax(s0, -hv * inv);
+                if (!(tau_bits >> j & 1u)) s0 = fmax(s0, -hv * inv);
                 act |= 1u << j;
             }
         }
     }
     if (__any_sync(kFull, viol)) return out;
+    s0 = warp_max(s0);
     __syncwarp();
-    // bits of the two tau rows in this lane's mask
-    unsigned tau_bits = 0;
-#pragma unroll
-    for (int j = 0; j < MR; ++j) {
-        const int r = lane + 32 * j;
-        if (tau && r > m + NX && r <= m + NX + 2) tau_bits |= 1u << j;
-    }
+    double obj;
     if (phase1 || mode == EHM_SX_ALIVE) {
-        // sigma column: -1 on every phase-1 row
+        // sigma column: -1 on every phase-1 row; the tau column is restored afterwards from
+        // registers (two rows at most)
         const unsigned act1 = act & ~tau_bits;
-        double keep[MR];
-#pragma unroll
-        for (int j = 0; j < MR; ++j) {
-            const int r = lane + 32 * j;
-            keep[j] = Gs[NB * MRP + r];
-            if (act1 >> j & 1u) Gs[NB * MRP + r] = -1.0;
+        double keep0 = 0.0;  // tau-column value of this lane's non-tau rows is 0
+        (void)keep0;
+#pragma unroll 1
+        for (int j = 0; j < MR; ++j)
+            if (act1 >> j & 1u) Gs[NB * MRP + lane + 32 * j] = -1.0;
+        for (int e = lane; e < NVS * NVS; e += 32) Hs[e] = 0.0;
+        if (lane < 16) {
+            fs[lane] = (lane == NB) ? 1.0 : 0.0;
+            zs[lane] = (lane == NB) ? s0 + 1.0 : 0.0;
         }
-        if (lane < 16) fs[lane] = (lane == NB) ? 1.0 : 0.0;
-        s0 = warp_max(s0);
         __syncwarp();
-        double z[NVS];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) z[k] = 0.0;
-        z[NB] = s0 + 1.0;
-        double obj;
-        int it;
-        const int st = ipm_solve<NVS, MR, false>(Gs, hs, act1, Hs, fs, red, z, obj, it, lane, &out.flops);
-        out.iters += it;
-        out.nsolves++;
+        const int st = run_ipm<NVS, MR>(ws, act1, lane, out, obj);
         if (st != 0) {
             out.status = -1;
             return out;
@@ -321,10 +324,15 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
             return out;
         }
         if (!(obj <= -EHM_TAU_INT)) return out;
-#pragma unroll
-        for (int j = 0; j < MR; ++j) {
-            const int r = lane + 32 * j;
-            if (act1 >> j & 1u) Gs[NB * MRP + r] = keep[j];
+#pragma unroll 1
+        for (int j = 0; j < MR; ++j)
+            if (act1 >> j & 1u) Gs[NB * MRP + lane + 32 * j] = 0.0;
+        // the row-state region was clobbered by the solver: reload the geometry scratch
+        for (int e = lane; e < (NX + 1) * NX; e += 32) Rs[e] = Rv[e];
+        __syncwarp();
+        for (int e = lane; e < NX * NX; e += 32) {
+            const int j = e / NX, i = e % NX;
+            Es[e] = Rs[(i + 1) * NX + j] - Rs[j];
         }
         __syncwarp();
     }
@@ -351,8 +359,7 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         MTs[e] = v;
     }
     __syncwarp();
-    // Mp into Ms
-    for (int e = lane; e < Y * Y; e += 32) {
+    for (int e = lane; e < Y * Y; e += 32) {  // Mp into Ms
         const int a = e / Y, b = e % Y;
         double v = 0.0;
 #pragma unroll
@@ -366,45 +373,27 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         if (lane < NB) v = fmax(2.0 * fabs(Ms[lane * Y + lane]), 2.0 * fabs(Ms[lane * Y + Y - 1]));
         cs = fmax(1.0, warp_max(v));
     }
-    const int nv = tau ? NVS : NB;
-    for (int e = lane; e < nv * nv; e += 32) {
-        const int a = e / nv, b = e % nv;
+    for (int e = lane; e < NVS * NVS; e += 32) {
+        const int a = e / NVS, b = e % NVS;
         Hs[e] = (a < NB && b < NB) ? 2.0 * Ms[a * Y + b] / cs : 0.0;
     }
-    if (lane < 16) fs[lane] = (lane < NB) ? 2.0 * Ms[lane * Y + Y - 1] / cs : (lane == NB ? 1.0 : 0.0);
-    __syncwarp();
-    double obj;
-    int it, st;
-    double zsol[NVS];
-    if (tau) {
-        double z[NVS];
-#pragma unroll
-        for (int k = 0; k < NVS; ++k) z[k] = 0.0;
-        st = ipm_solve<NVS, MR, true>(Gs, hs, act, Hs, fs, red, z, obj, it, lane, &out.flops);
-#pragma unroll
-        for (int k = 0; k < NVS; ++k) zsol[k] = z[k];
-    } else {
-        double z[NB];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) z[k] = 0.0;
-        st = ipm_solve<NB, MR, true>(Gs, hs, act, Hs, fs, red, z, obj, it, lane, &out.flops);
-#pragma unroll
-        for (int k = 0; k < NB; ++k) zsol[k] = z[k];
-        zsol[NB] = 0.0;
+    if (lane < 16) {
+        fs[lane] = (lane < NB) ? 2.0 * Ms[lane * Y + Y - 1] / cs : ((lane == NB && tau) ? 1.0 : 0.0);
+        zs[lane] = 0.0;
     }
-    out.iters += it;
-    out.nsolves++;
+    __syncwarp();
+    const int st = run_ipm<NVS, MR>(ws, act, lane, out, obj);
     if (st != 0) {
         out.status = -1;
         return out;
     }
     out.status = 1;
     out.val = cs * obj + cst;
-    if (sol != nullptr && lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NX; ++i) sol[i] = zsol[U + i];
-        sol[NX] = tau ? out.val - zsol[NB] * cs : out.val;
+    if (sol != nullptr) {
+        if (lane < NX) sol[lane] = zs[U + lane];
+        if (lane == NX) sol[NX] = tau ? out.val - zs[NB] * cs : out.val;
     }
+    __syncwarp();
     return out;
 }
 

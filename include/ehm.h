@@ -33,7 +33,6 @@ extern "C" {
 
 /* Canonical tolerances; identical, by specification, to oracle/ehm_oracle.h */
 #define EHM_TOL_IPM   1e-9
-#define EHM_TOL_DUAL  1e-2
 #define EHM_TAU_INT   1e-7
 #define EHM_TAU_CONST 1e-7
 #define EHM_ZERO_ROW  1e-13
@@ -117,7 +116,29 @@ typedef struct {
 
 typedef struct ehm_partition ehm_partition;
 
-/* roots: host (nroots,(n+1),n).  Runs until the frontier is empty (or node_budget). */
+/* Resumable form: create the node store / frontier with the root simplices (host
+ * (nroots,(n+1),n); nroots may be 0 for a rank that only receives work), then advance by at
+ * most max_waves waves (<= 0: until the frontier is empty or node_budget is hit).  stats are
+ * cumulative since creation; stats.open_left > 0 means there is work left. */
+int ehm_partition_create(ehm_problem *p, int nroots, const double *roots,
+                         const ehm_partition_opts *opts, ehm_partition **out);
+/* optional, right after create: global ids of the root simplices (default 0..nroots-1); they
+ * are inherited by all descendants and travel with exported records */
+int ehm_partition_set_root_ids(ehm_partition *t, int nroots, const int32_t *ids);
+int ehm_partition_advance(ehm_partition *t, int64_t max_waves, ehm_partition_stats *stats);
+/* Frontier exchange between ranks (replaces the worker->scheduler->worker task hand-over,
+ * lib/worker.py:232-236, lib/scheduler.py:515-523).  export pops the k OLDEST entries into
+ * caller-owned DEVICE buffers: d_meta int32[k][6] {node, cand, depth, root_id, skip, 0},
+ * d_geom f64[k][(n+1)n+(n+1)+(n+1)nu] (vertices, vertex costs, vertex inputs), d_lb
+ * f32[k][ncand]; the exported nodes are marked closed=2.  import appends k received records as
+ * new nodes (origin = (d_origin_rank[e], meta node id)) and pushes them on the frontier. */
+int ehm_partition_export(ehm_partition *t, int k, int32_t *d_meta, double *d_geom, float *d_lb);
+int ehm_partition_import(ehm_partition *t, int k, const int32_t *d_meta, const double *d_geom,
+                         const float *d_lb, const int32_t *d_origin_rank);
+/* origin int32[nnodes][2] (rank, node) of imported nodes, -1 for local ones (HOST buffer) */
+int ehm_partition_fetch_origin(ehm_partition *t, int32_t *origin);
+/* One-shot form = create + advance(0).
+ * roots: host (nroots,(n+1),n).  Runs until the frontier is empty (or node_budget). */
 int ehm_partition_run(ehm_problem *p, int nroots, const double *roots,
                       const ehm_partition_opts *opts, ehm_partition **out,
                       ehm_partition_stats *stats);

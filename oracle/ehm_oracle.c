@@ -146,9 +146,9 @@ static int qp_solve(int nv, int m, const double *H, const double *f, const doubl
         /* Every step scales the dual residual by exactly (1 - alpha (1 - sigma)); the value
          * measured above additionally carries the round-off of the normal equations (up to
          * ~1e-4 relative once lam/s spans 20+ orders), so convergence is tested on the
-         * propagated value rho*rd0 and the measured one only as a coarse guard. */
+         * propagated value rho*rd0; the measured one is not used. */
+        (void)rdmax;
         if (rpmax <= EHMO_TOL_IPM * (1 + zmax) && rho * rd0 <= EHMO_TOL_IPM * (1 + fmax + lmax) &&
-            rdmax <= EHMO_TOL_DUAL * (1 + fmax + lmax) &&
             mu <= EHMO_TOL_IPM * (1 + fabs(obj))) {
             status = 0;
             break;

@@ -34,8 +34,6 @@ typedef struct ehmo_problem ehmo_problem;
 
 /* Canonical tolerances (shared, by specification, with the CUDA engine). */
 #define EHMO_TOL_IPM   1e-9   /* primal residual and duality gap s'lam, relative              */
-#define EHMO_TOL_DUAL  1e-2   /* dual residual guard, relative to 1+|f|+|lam| (the normal-
-                                 equation round-off floor sits near 1e-6 on thin feasible sets) */
 #define EHMO_TAU_INT   1e-7   /* a candidate is alive iff some point has all normalised
                                  slacks >= TAU_INT (phase-1 optimum sigma* <= -TAU_INT)      */
 #define EHMO_TAU_CONST 1e-7   /* constant rows (no variable coefficient) may be violated by

@@ -1,0 +1,165 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo process group, a fake
+engine with the same interface as the CUDA one (no compute calls need a GPU)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_rebalance_plan_properties():
+    from explicit_hybrid_mpc_b200.partition import rebalance_plan
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        world = int(rng.integers(2, 9))
+        sizes = rng.integers(0, 20000, world) * (rng.random(world) < 0.7)
+        plan = rebalance_plan(sizes, 512)
+        assert plan.shape == (world, world) and (plan >= 0).all() and (np.diag(plan) == 0).all()
+        after = sizes - plan.sum(axis=1) + plan.sum(axis=0)
+        assert (after >= 0).all() and after.sum() == sizes.sum()
+        if plan.sum():
+            # senders stay at or above the mean, receivers do not overshoot it
+            mean = sizes.sum() / world
+            assert (after[plan.sum(axis=1) > 0] >= np.floor(mean) - 1).all()
+            assert (after[plan.sum(axis=0) > 0] <= np.ceil(mean) + 1).all()
+    assert rebalance_plan([5000, 4500, 4000, 4800], 512).sum() == 0      # balanced: nothing moves
+    assert rebalance_plan([0, 0, 0], 512).sum() == 0
+    p = rebalance_plan([10000, 0, 50, 3000], 512)
+    assert p[0].sum() > 6000 and p[1:].sum() == 0
+
+
+class FakeEngine:
+    """Deterministic stand-in for ``partition._Engine``: every frontier record is a 1-simplex
+    [a,b]; a node with depth < its root's target depth splits in two, otherwise it closes."""
+    n, nu, ncand = 1, 1, 4
+
+    def __init__(self, oracle, roots, wave=0, max_nodes=0, max_frontier=0, node_budget=0, verbose=0,
+                 root_ids=None):
+        self.oracle = oracle
+        self.opts = type('O', (), dict(wave=wave))()
+        roots = np.asarray(roots, dtype=float).reshape(-1, 2, 1)
+        ids = list(range(len(roots))) if root_ids is None else [int(i) for i in root_ids]
+        self.nodes = []          # dicts
+        self.frontier = []
+        for r, rid in zip(roots, ids):
+            self._new(r, 0, rid, (-1, -1))
+            self.frontier.append(len(self.nodes) - 1)
+        self.stats = type('S', (), dict(open_left=len(self.frontier), nnodes=len(self.nodes)))()
+
+    def _new(self, verts, depth, rid, origin):
+        self.nodes.append(dict(v=np.array(verts, float).reshape(2, 1), depth=depth, rid=rid, left=-1,
+                               right=-1, closed=0, origin=origin))
+
+    def geom_width(self):
+        return 2 + 2 + 2
+
+    def advance(self, max_waves=0):
+        waves = 0
+        while self.frontier and (max_waves <= 0 or waves < max_waves):
+            batch, self.frontier = self.frontier[-4:], self.frontier[:-4]
+            for i in batch:
+                nd = self.nodes[i]
+                target = 3 + nd['rid'] % 4          # unbalanced sub-trees
+                if nd['depth'] >= target:
+                    nd['closed'] = 1
+                    continue
+                a, b = nd['v'][0, 0], nd['v'][1, 0]
+                m = (a + b) / 2
+                for seg in ([a, m], [m, b]):
+                    self._new(seg, nd['depth'] + 1, nd['rid'], (-1, -1))
+                nd['left'], nd['right'] = len(self.nodes) - 2, len(self.nodes) - 1
+                self.frontier += [len(self.nodes) - 2, len(self.nodes) - 1]
+            waves += 1
+        self.stats.open_left, self.stats.nnodes = len(self.frontier), len(self.nodes)
+        return len(self.frontier)
+
+    def export(self, k):
+        ids, self.frontier = self.frontier[:k], self.frontier[k:]
+        meta = torch.tensor([[i, 0, self.nodes[i]['depth'], self.nodes[i]['rid'], 0, 0] for i in ids],
+                            dtype=torch.int32).reshape(-1, 6)
+        geom = torch.tensor([list(self.nodes[i]['v'].ravel()) + [0, 0, 0, 0] for i in ids],
+                            dtype=torch.float64).reshape(-1, 6)
+        for i in ids:
+            self.nodes[i]['closed'] = 2
+        self.stats.open_left = len(self.frontier)
+        return meta, geom, torch.zeros(len(ids), self.ncand, dtype=torch.float32)
+
+    def import_(self, meta, geom, lb, origin_rank):
+        for e in range(meta.shape[0]):
+            self._new(geom[e, :2].numpy(), int(meta[e, 2]), int(meta[e, 3]),
+                      (int(origin_rank[e]), int(meta[e, 0])))
+            self.frontier.append(len(self.nodes) - 1)
+        self.stats.open_left, self.stats.nnodes = len(self.frontier), len(self.nodes)
+
+    def fetch(self, with_origin=False):
+        N = self.nodes
+        arr = dict(left=np.array([x['left'] for x in N], np.int32), right=np.array([x['right'] for x in N], np.int32),
+                   root_id=np.array([x['rid'] for x in N], np.int32), depth=np.array([x['depth'] for x in N], np.int32),
+                   cand=np.zeros(len(N), np.int32), closed=np.array([x['closed'] for x in N], np.uint8),
+                   vertices=np.array([x['v'] for x in N]).reshape(-1, 2, 1), vcost=np.zeros((len(N), 2)),
+                   vinput=np.zeros((len(N), 2, 1)))
+        if with_origin:
+            arr['origin'] = np.array([x['origin'] for x in N], np.int32).reshape(-1, 2)
+        return arr
+
+    def stats_dict(self):
+        return dict(nnodes=len(self.nodes), nleaves=sum(1 for x in self.nodes if x['closed'] == 1))
+
+    def close(self):
+        pass
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from explicit_hybrid_mpc_b200 import partition as P
+    oracle = type('Orc', (), dict(device=torch.device('cpu'), n=1, nu=1, ncand=4,
+                                  pb=type('PB', (), dict(u_scale=np.ones(1)))()))()
+    nroots = 7
+    roots = np.array([[[float(i)], [float(i) + 1.0 + 0.1 * i]] for i in range(nroots)])
+    res, info = P.partition_distributed(oracle, roots, waves_per_round=1, engine_cls=FakeEngine,
+                                        fill_depth=3)
+    if rank == 0:
+        q.put((dict(left=res.left, right=res.right, root_id=res.root_id, depth=res.depth,
+                    closed=res.closed, vertices=res.vertices), info['rounds']))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_partition_distributed_gloo_world2():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out, rounds = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # reference: the same fake partition on one rank
+    ref = FakeEngine(None, np.array([[[float(i)], [float(i) + 1.0 + 0.1 * i]] for i in range(7)]))
+    ref.advance(0)
+    r = ref.fetch()
+    assert len(out['left']) == len(r['left'])                 # exported duplicates were removed
+    leaves_o = np.nonzero(out['left'] < 0)[0]
+    leaves_r = np.nonzero(r['left'] < 0)[0]
+    assert len(leaves_o) == len(leaves_r) and (out['closed'][leaves_o] == 1).all()
+    key = lambda a, idx: sorted((int(a['root_id'][i]), int(a['depth'][i]), float(a['vertices'][i][0, 0]),
+                                 float(a['vertices'][i][1, 0])) for i in idx)
+    assert key(out, leaves_o) == key(r, leaves_r)             # identical leaf sets
+    # every non-leaf has two valid children, every node except the roots exactly one parent
+    inner = np.nonzero(out['left'] >= 0)[0]
+    ch = np.concatenate([out['left'][inner], out['right'][inner]])
+    assert len(set(ch.tolist())) == len(ch) == len(out['left']) - 7
+    assert rounds >= 1                                        # the rebalance path was exercised
