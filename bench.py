@@ -32,7 +32,8 @@ sys.path.insert(0, ROOT)
 ABS_FRAC, EPS_R = 0.25, 1.0
 EPS_A_FIXTURE = 19.21220798973866   # max_v P_theta(0.25 v).J, recomputed on the GPU at start-up
 METRIC = 'simplices partitioned/sec (eps-converged leaves)'
-# bounded CPU sample: the 12 cheapest root simplices of the workload (by leaf count)
+# bounded CPU sample: the 6 cheapest root simplices of the workload (by leaf count); the CPU
+# oracle shares the work of ALL sampled roots over all threads (shared LIFO task queue)
 CPU_SAMPLE_ROOTS = None  # filled from tests/golden/pendulum_root_leafcounts.json when present
 
 
@@ -73,7 +74,7 @@ def _cpu_sample():
     if os.path.exists(p):
         cnt = json.load(open(p))['leaves_per_root']
         order = np.argsort(cnt)
-        return [int(i) for i in order[:12]]
+        return [int(i) for i in order[:6]]
     return [22, 23, 24, 25]
 
 
@@ -96,10 +97,10 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     sample = _cpu_sample()
-    threads = min(cores, len(sample))
+    threads = cores
     vals, ms = [], []
     for i in range(args.warmup + args.steps):
-        r = cpu_leg(threads, sample if i >= args.warmup else sample[:max(1, threads // 2)])
+        r = cpu_leg(threads, sample if i >= args.warmup else sample[:1])
         if i >= args.warmup:
             vals.append(r)
             ms.append(r['seconds'] * 1e3)
@@ -157,21 +158,30 @@ def main():
     eps_a = max(orc.P_theta(ABS_FRAC * v)[2] for v in box)
     assert abs(eps_a - EPS_A_FIXTURE) <= 1e-6 * EPS_A_FIXTURE, eps_a
     orc.set_eps(eps_a, EPS_R)
-    # shard the root simplices over the ranks (largest volume first, round robin)
-    from explicit_hybrid_mpc_b200.tools import simplex_volume
-    order = np.argsort([-simplex_volume(r) for r in roots_all], kind='stable')
-    mine = np.sort(order[rank::world])
-    roots = np.ascontiguousarray(roots_all[mine])
+    from explicit_hybrid_mpc_b200.partition import partition_distributed
+    roots = roots_all           # world == 1: everything; world > 1: sharded inside the driver
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
 
     def step():
         flush.fill_(1)                      # evict L2 between timed iterations
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
-        res = partition(orc, roots)
+        if world == 1:
+            res = partition(orc, roots)
+            info = dict(exchange_s=0.0, rounds=0, records_sent=0)
+        else:
+            # one partition job over all ranks: sharded frontier + all-to-all rebalance; the
+            # stitched tree is gathered to rank 0 inside the timed region (end-to-end)
+            res, info = partition_distributed(orc, roots, gather=True)
+            if res is None:
+                res = type('R', (), dict(stats=info['stats'], nnodes=info['stats']['nnodes']))()
+            else:
+                res.stats = info['stats']
         torch.cuda.synchronize()
-        return res, time.perf_counter() - t0
+        return res, time.perf_counter() - t0, info
 
     for _ in range(args.warmup):
         step()
@@ -183,12 +193,15 @@ def main():
     th.start()
     l0 = _capi.lib().ehm_kernel_launches()
     t_begin = time.perf_counter()
-    dev_ms, walls, results = [], [], []
+    dev_ms, walls, results, xch = [], [], [], []
     for _ in range(args.steps):
-        res, wall = step()
-        dev_ms.append(res.stats['device_ms'])
+        res, wall, info = step()
+        # device time: one GPU = CUDA events around the loop inside the library; N GPUs = CUDA
+        # events around the whole sharded loop of this rank (waits for the other ranks included)
+        dev_ms.append(info['loop_device_ms'] if world > 1 else res.stats['device_ms'])
         walls.append(wall)
         results.append(res)
+        xch.append(info)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -199,10 +212,10 @@ def main():
 
     res = results[-1]
     leaves = sum(r.stats['nleaves'] for r in results)
-    nn = res.nnodes
+    nn = res.stats['nnodes']
     n, nu = 4, 1
     d2h = nn * (5 * 4 + 1 + 8 * ((n + 1) * n + (n + 1) + (n + 1) * nu))
-    h2d = roots.nbytes
+    h2d = roots.nbytes // world
     tot = torch.tensor([float(leaves), float(sum(r.stats['nsolves'] for r in results)),
                         float(launches)], dtype=torch.float64, device='cuda')
     mx = torch.tensor([sum(dev_ms) * 1e-3, sum(walls)], dtype=torch.float64, device='cuda')
@@ -256,7 +269,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         sample = _cpu_sample()
-        threads = min(os.cpu_count() or 1, len(sample))
+        threads = os.cpu_count() or 1
         c = cpu_leg(threads, sample)
         cpu = dict(value=c['value'], unit='leaves/s', cores=threads, kind='port',
                    sample='%d cheapest root simplices of the same workload (%d leaves, %.1f s)'
@@ -271,7 +284,10 @@ def main():
                              '(BASELINE.json configs[1])',
                     eps_a=eps_a, leaves_per_step=leaves_all / args.steps,
                     nodes_per_step=nn if world == 1 else None,
-                    parallelism='root simplices sharded over %d rank(s), no data-path collective' % world,
+                    parallelism=('single GPU' if world == 1 else 'frontier sharded over %d ranks: roots dealt '
+                                 'round-robin, NCCL all-gather of depths every 2 waves, all-to-all of '
+                                 'frontier records only when depths diverge (%d rounds, %d records in the '
+                                 'last step)' % (world, xch[-1]['rounds'], xch[-1]['records_sent'])),
                     l2='flushed between timed iterations (256 MiB write)'),
         e2e=dict(value=e2e, unit='leaves/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
         oracle_solves_per_s=solves_all / dev_s,

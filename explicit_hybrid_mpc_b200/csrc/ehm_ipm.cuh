@@ -128,27 +128,89 @@ struct IpmWs {
     static constexpr int oZ = oF + 16;           // z in/out (16)
     static constexpr int oRed = oZ + 16;         // reduction scratch / packed K / packed L (64)
     static constexpr int oOut = oRed + 64;       // [0] objective [1] iterations [2] flops (8)
-    static constexpr int kDoubles = oOut + 8;
+    static constexpr int oLs = oOut + 8;         // packed Cholesky factor / working matrix (64)
+    static constexpr int oD0 = oLs + 64;         // original diagonal of K (16)
+    static constexpr int oScr = oD0 + 16;        // 8 x 33 transposition scratch of the reductions
+    static constexpr int kDoubles = oScr + 8 * 33;
 };
+
+// Warp sum of 8 per-lane values through shared memory: the 8x32 partials are transposed through
+// a padded 8x33 scratch (2-way bank conflicts only, the minimum for 64-bit words), lane L adds 8
+// of the 32 partials of value L/4, two shuffle stages finish.  Returns the sum of value L/4.
+// Shared memory instead of a shuffle tree because every 64-bit shuffle costs ~12 SASS
+// instructions here; the unrolled reduce-scatter of the 55 normal-matrix entries alone was
+// 2.7k instructions and pushed the solver loop out of the instruction cache (profiles/).
+__device__ __noinline__ double chunk_reduce8(double v0, double v1, double v2, double v3, double v4,
+                                              double v5, double v6, double v7, double *scr, int lane)
+{
+    scr[0 * 33 + lane] = v0;
+    scr[1 * 33 + lane] = v1;
+    scr[2 * 33 + lane] = v2;
+    scr[3 * 33 + lane] = v3;
+    scr[4 * 33 + lane] = v4;
+    scr[5 * 33 + lane] = v5;
+    scr[6 * 33 + lane] = v6;
+    scr[7 * 33 + lane] = v7;
+    __syncwarp();
+    const double *q = scr + (lane >> 2) * 33 + (lane & 3) * 8;
+    double a = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+    a += __shfl_xor_sync(kFull, a, 1);
+    a += __shfl_xor_sync(kFull, a, 2);
+    __syncwarp();
+    return a;
+}
+
+// Sum CNT (<= 8*NCH) per-lane partials v[] over the warp into out[0..CNT) (shared memory).
+template <int NCH, int P>
+__device__ __forceinline__ void reduce_chunks(const double (&v)[P], double *out, int cnt, double *scr, int lane)
+{
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const double r = chunk_reduce8(v[8 * c + 0], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3], v[8 * c + 4],
+                                       v[8 * c + 5], v[8 * c + 6], v[8 * c + 7], scr, lane);
+        const int idx = 8 * c + (lane >> 2);
+        if ((lane & 3) == 0 && idx < cnt) out[idx] = r;
+    }
+    __syncwarp();
+}
+
+// min over the warp of the fractions num/den (den > 0), compared by cross-multiplication so
+// that the row loops need no division; returns the winning (num, den).
+__device__ __forceinline__ void warp_min_frac(double &num, double &den)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double n2 = __shfl_xor_sync(kFull, num, o), d2 = __shfl_xor_sync(kFull, den, o);
+        if (n2 * den < num * d2) {
+            num = n2;
+            den = d2;
+        }
+    }
+}
 
 // Solve  min 0.5 z'Hz + f'z  s.t.  G z <= h  with one warp.  `w` = base of an IpmWs block:
 // G, h, Hs, f and the primal start z must be filled in; act: bit j set <=> row lane+32*j takes
-// part (normalised, non-constant row).  On return z holds the solution, out[0..2] the
-// objective / iteration count / algorithmic flops.  returns 0 converged, 1 iteration limit,
-// 2 numerical breakdown.
+// part (normalised, non-constant row); rows that do not take part must hold G = 0, h = 1.
+// On return z holds the solution, out[0..2] the objective / iteration count / algorithmic
+// flops.  returns 0 converged, 1 iteration limit, 2 numerical breakdown.
+//
+// Row passes handle TWO rows per trip of a rolled loop (independent dependency chains: the
+// solver is latency bound with 7 resident warps per SM), are branch free (rows that do not
+// take part carry s = 1, lam = 0 and a zero mask) and contain no division: 1/s is formed once
+// per row and iteration, step-length ratios are compared by cross-multiplication.
 template <int NV, int MR>
 __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
 {
     using W = IpmWs<NV, MR>;
     constexpr int MRP = W::MRP;
     constexpr int NK = NV * (NV + 1) / 2;
-    constexpr int PK = pow2_ge(NK);
-    constexpr int PV = pow2_ge(NV);
+    constexpr int PK = 8 * ((NK + 7) / 8);   // accumulators padded to whole 8-value chunks
+    constexpr int PV = 8 * ((NV + 7) / 8);
     const double *__restrict__ Gs = w + W::oG;
     const double *__restrict__ hs = w + W::oH;
     double *sv = w + W::oS, *lv = w + W::oL, *av = w + W::oA, *bv = w + W::oB;
     const double *__restrict__ Hs = w + W::oHs;
-    double *red = w + W::oRed;
+    double *red = w + W::oRed, *Ls = w + W::oLs, *D0 = w + W::oD0, *scr = w + W::oScr;
     double z[NV], f[NV];
     double fmx = 0.0;
 #pragma unroll
@@ -166,8 +228,14 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         for (int k = 0; k < PV; ++k) gl[k] = 0.0;
 #pragma unroll 1
         for (int j = 0; j < MR; ++j) {
-            if (!(act >> j & 1u)) continue;
             const int r = lane + 32 * j;
+            if (!(act >> j & 1u)) {
+                sv[r] = 1.0;
+                lv[r] = 0.0;
+                av[r] = 1.0;
+                bv[r] = 0.0;
+                continue;
+            }
             double g[NV], gz = 0.0;
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
@@ -181,49 +249,54 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
 #pragma unroll
             for (int k = 0; k < NV; ++k) gl[k] = fma(g[k], l, gl[k]);
         }
-        warp_reduce_to_smem<PV>(gl, red, NV, lane);
+        reduce_chunks<PV / 8>(gl, red, NV, scr, lane);
         double m = 0.0;
+        if (lane < NV) {
+            double hz = w[W::oF + lane] + red[lane];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double hz = f[k] + red[k];
-#pragma unroll
-            for (int l = 0; l < NV; ++l) hz = fma(Hs[k * NV + l], z[l], hz);
-            m = fmax(m, fabs(hz));
+            for (int l = 0; l < NV; ++l) hz = fma(Hs[lane * NV + l], z[l], hz);
+            m = fabs(hz);
         }
-        rd0 = m;
+        rd0 = warp_max(m);
         __syncwarp();
     }
+    // masks of the two rows handled per loop trip
     int status = 1, it = 0;
     double rho = 1.0, obj = 0.0;
 #pragma unroll 1
     for (it = 0; it <= EHM_MAX_ITER; ++it) {
-        // ---- pass A: primal residual, gap, normal matrix ------------------------------------
+        // ---- pass A: primal residual, gap, 1/s, normal matrix -------------------------------
         double acc[PK];
 #pragma unroll
         for (int k = 0; k < PK; ++k) acc[k] = 0.0;
         double mu = 0.0, rpm = 0.0, lmx = 0.0;
 #pragma unroll 1
-        for (int j = 0; j < MR; ++j) {
-            if (!(act >> j & 1u)) continue;
-            const int r = lane + 32 * j;
-            double g[NV], gz = 0.0;
+        for (int j = 0; j < MR; j += 2) {
+            const bool on1 = (j + 1 < MR);
+            const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
+            const double m1 = on1 ? 1.0 : 0.0;
+            double g0[NV], g1[NV], gz0 = 0.0, gz1 = 0.0;
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-                g[k] = Gs[k * MRP + r];
-                gz = fma(g[k], z[k], gz);
+                g0[k] = Gs[k * MRP + r0];
+                g1[k] = Gs[k * MRP + r1];
+                gz0 = fma(g0[k], z[k], gz0);
+                gz1 = fma(g1[k], z[k], gz1);
             }
-            const double s = sv[r], l = lv[r];
-            const double rp = gz + s - hs[r];
-            av[r] = rp;
-            rpm = fmax(rpm, fabs(rp));
-            mu = fma(s, l, mu);
-            lmx = fmax(lmx, l);
-            const double wt = l / s;
+            const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0], l1 = lv[r1] * m1;
+            const double rs0 = 1.0 / s0, rs1 = 1.0 / s1;
+            av[r0] = rs0;
+            if (on1) av[r1] = rs1;
+            rpm = fmax(rpm, fmax(fabs(gz0 + s0 - hs[r0]), m1 * fabs(gz1 + s1 - hs[r1])));
+            mu = fma(s0, l0, fma(s1, l1, mu));
+            lmx = fmax(lmx, fmax(l0, l1));
+            const double wt0 = l0 * rs0, wt1 = l1 * rs1;
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-                const double gw = wt * g[k];
+                const double gw0 = wt0 * g0[k], gw1 = wt1 * g1[k];
 #pragma unroll
-                for (int q = 0; q <= k; ++q) acc[tri(k, q)] = fma(gw, g[q], acc[tri(k, q)]);
+                for (int q = 0; q <= k; ++q)
+                    acc[tri(k, q)] = fma(gw0, g0[q], fma(gw1, g1[q], acc[tri(k, q)]));
             }
         }
         mu = warp_sum(mu);
@@ -260,16 +333,16 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         }
         if (it == EHM_MAX_ITER) break;
         const double mu_mean = mu / mact;
-        // ---- K -> packed scratch -> lane-parallel Cholesky -> replicated factor --------------
-        warp_reduce_to_smem<PK>(acc, red, NK, lane);
+        // ---- K -> packed scratch -> lane-parallel Cholesky (rows in registers, pivot rows
+        //      broadcast by shuffle) -> factor replicated into every lane --------------------
+        reduce_chunks<PK / 8>(acc, red, NK, scr, lane);
         double L[NK], inv[NV];
         {
             double Lr[NV], d0 = 1.0;
             const int li = lane < NV ? lane : 0;
 #pragma unroll
-            for (int k = 0; k < NV; ++k)
-                Lr[k] = (lane < NV && k <= lane) ? red[tri(li, k)] + Hs[li * NV + k] : 0.0;
-            if (lane < NV) d0 = red[tri(li, li)] + Hs[li * NV + li];
+            for (int k = 0; k < NV; ++k) Lr[k] = (k <= li) ? red[tri(li, k)] + Hs[li * NV + k] : 0.0;
+            d0 = red[tri(li, li)] + Hs[li * NV + li];
             __syncwarp();
             bool bad = false;
 #pragma unroll
@@ -277,25 +350,22 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                 double v = Lr[j];
 #pragma unroll
                 for (int k = 0; k < j; ++k) v = fma(-Lr[k], __shfl_sync(kFull, Lr[k], j), v);
-                const double d = __shfl_sync(kFull, v, j);
+                double d = __shfl_sync(kFull, v, j);
                 const double dd0 = __shfl_sync(kFull, d0, j);
                 if (!isfinite(d)) bad = true;
-                const double2 pv = chol_pivot(d, dd0);
-                inv[j] = pv.y;
-                Lr[j] = (lane == j) ? pv.x : ((lane > j && lane < NV) ? v * pv.y : 0.0);
+                if (d <= 1e-13 * dd0 || dd0 <= 0.0) d = 1e100;   // pivot guard (oracle: cholesky)
+                const double iv = rsqrt(d);
+                inv[j] = iv;
+                Lr[j] = (lane == j) ? d * iv : v * iv;
+                if (lane >= j && lane < NV) Ls[tri(li, j)] = Lr[j];
             }
             if (bad) {
                 status = 2;
                 break;
             }
-            if (lane < NV) {
-#pragma unroll
-                for (int k = 0; k < NV; ++k)
-                    if (k <= lane) red[tri(li, k)] = Lr[k];
-            }
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < NK; ++k) L[k] = red[k];
+            for (int k = 0; k < NK; ++k) L[k] = Ls[k];
             __syncwarp();
         }
         // ---- predictor (trip 0) and corrector (trip 1) share one code path -------------------
@@ -303,66 +373,98 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         double dz[NV];
 #pragma unroll 1
         for (int trip = 0; trip < 2; ++trip) {
+            const double tsel = trip ? 1.0 : 0.0;
             double rh[PV];
 #pragma unroll
             for (int k = 0; k < PV; ++k) rh[k] = 0.0;
 #pragma unroll 1
-            for (int j = 0; j < MR; ++j) {
-                if (!(act >> j & 1u)) continue;
-                const int r = lane + 32 * j;
-                const double s = sv[r], l = lv[r], rp = av[r];
+            for (int j = 0; j < MR; j += 2) {
+                const bool on1 = (j + 1 < MR);
+                const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
+                const double m0 = (act >> j & 1u) ? 1.0 : 0.0;
+                const double m1 = (on1 && (act >> (j + 1) & 1u)) ? 1.0 : 0.0;
+                double g0[NV], g1[NV], gz0 = 0.0, gz1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    g0[k] = Gs[k * MRP + r0];
+                    g1[k] = Gs[k * MRP + r1];
+                    gz0 = fma(g0[k], z[k], gz0);
+                    gz1 = fma(g1[k], z[k], gz1);
+                }
+                const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0], l1 = lv[r1];
+                const double rp0 = gz0 + s0 - hs[r0], rp1 = gz1 + s1 - hs[r1];
                 // rc: s.lam (predictor) or s.lam + ds_aff.dl_aff - sigma mu (corrector)
-                double rc = s * l;
+                const double rc0 = m0 * fma(tsel, bv[r0] - sig * mu_mean, s0 * l0);
+                const double rc1 = m1 * fma(tsel, bv[r1] - sig * mu_mean, s1 * l1);
                 if (trip) {
-                    rc = rc + bv[r] - sig * mu_mean;
-                    bv[r] = rc;
+                    bv[r0] = rc0;
+                    if (on1) bv[r1] = rc1;
                 }
                 // rhs = -c (Hz+f) - G'(c lam + t),  t = (lam c rp - rc)/s
-                const double q = fma(cres, l, (l * cres * rp - rc) / s);
+                const double q0 = fma(cres, l0, (l0 * cres * rp0 - rc0) * av[r0]);
+                const double q1 = m1 * fma(cres, l1, (l1 * cres * rp1 - rc1) * av[r1]);
 #pragma unroll
-                for (int k = 0; k < NV; ++k) rh[k] = fma(Gs[k * MRP + r], q, rh[k]);
+                for (int k = 0; k < NV; ++k) rh[k] = fma(g0[k], q0, fma(g1[k], q1, rh[k]));
             }
-            warp_reduce_to_smem<PV>(rh, red, NV, lane);
+            reduce_chunks<PV / 8>(rh, red, NV, scr, lane);
 #pragma unroll
             for (int k = 0; k < NV; ++k) dz[k] = -cres * hzf[k] - red[k];
             __syncwarp();
-            // triangular solves with the replicated factor
+            // column-oriented triangular solves with the replicated factor (chain length 2/step)
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                double v = dz[i];
+            for (int k = 0; k < NV; ++k) {
+                dz[k] *= inv[k];
 #pragma unroll
-                for (int k = 0; k < i; ++k) v = fma(-L[tri(i, k)], dz[k], v);
-                dz[i] = v * inv[i];
+                for (int i = k + 1; i < NV; ++i) dz[i] = fma(-L[tri(i, k)], dz[k], dz[i]);
             }
 #pragma unroll
-            for (int i = NV - 1; i >= 0; --i) {
-                double v = dz[i];
+            for (int k = NV - 1; k >= 0; --k) {
+                dz[k] *= inv[k];
 #pragma unroll
-                for (int k = i + 1; k < NV; ++k) v = fma(-L[tri(k, i)], dz[k], v);
-                dz[i] = v * inv[i];
+                for (int i = 0; i < k; ++i) dz[i] = fma(-L[tri(k, i)], dz[k], dz[i]);
             }
-            double amax = 1e300;
+            // step to the boundary: min over rows of s/(-ds) and lam/(-dl), as fractions
+            double an = 1.0, ad = 1e-300;   // num/den = "infinite" step
+            an = 1e300;
+            ad = 1.0;
 #pragma unroll 1
-            for (int j = 0; j < MR; ++j) {
-                if (!(act >> j & 1u)) continue;
-                const int r = lane + 32 * j;
-                double gdz = 0.0;
+            for (int j = 0; j < MR; j += 2) {
+                const bool on1 = (j + 1 < MR);
+                const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
+                const double m1 = (on1 && (act >> (j + 1) & 1u)) ? 1.0 : 0.0;
+                const double m0 = (act >> j & 1u) ? 1.0 : 0.0;
+                double gz0 = 0.0, gz1 = 0.0, gd0 = 0.0, gd1 = 0.0;
 #pragma unroll
-                for (int k = 0; k < NV; ++k) gdz = fma(Gs[k * MRP + r], dz[k], gdz);
-                const double s = sv[r], l = lv[r];
-                const double rc = trip ? bv[r] : s * l;
-                const double ds = -cres * av[r] - gdz;
-                const double dl = (-rc - l * ds) / s;
-                if (ds < 0.0) amax = fmin(amax, -s / ds);
-                if (dl < 0.0) amax = fmin(amax, -l / dl);
+                for (int k = 0; k < NV; ++k) {
+                    const double a0 = Gs[k * MRP + r0], a1 = Gs[k * MRP + r1];
+                    gz0 = fma(a0, z[k], gz0);
+                    gz1 = fma(a1, z[k], gz1);
+                    gd0 = fma(a0, dz[k], gd0);
+                    gd1 = fma(a1, dz[k], gd1);
+                }
+                const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0], l1 = lv[r1];
+                const double rp0 = gz0 + s0 - hs[r0], rp1 = gz1 + s1 - hs[r1];
+                const double rc0 = trip ? bv[r0] : s0 * l0, rc1 = trip ? bv[r1] : s1 * l1;
+                const double ds0 = m0 * (-cres * rp0 - gd0), ds1 = m1 * (-cres * rp1 - gd1);
+                const double dl0 = m0 * (-rc0 - l0 * ds0) * av[r0], dl1 = m1 * (-rc1 - l1 * ds1) * av[r1];
+                if (ds0 < 0.0 && s0 * ad < an * (-ds0)) { an = s0; ad = -ds0; }
+                if (dl0 < 0.0 && l0 * ad < an * (-dl0)) { an = l0; ad = -dl0; }
+                if (ds1 < 0.0 && s1 * ad < an * (-ds1)) { an = s1; ad = -ds1; }
+                if (dl1 < 0.0 && l1 * ad < an * (-dl1)) { an = l1; ad = -dl1; }
                 if (trip) {
-                    av[r] = ds;
-                    bv[r] = dl;
+                    av[r0] = ds0;
+                    bv[r0] = dl0;
+                    if (on1) {
+                        av[r1] = ds1;
+                        bv[r1] = dl1;
+                    }
                 } else {
-                    bv[r] = ds * dl;
+                    bv[r0] = ds0 * dl0;
+                    if (on1) bv[r1] = ds1 * dl1;
                 }
             }
-            amax = warp_min(amax);
+            warp_min_frac(an, ad);
+            const double amax = an / ad;
             if (trip == 0) {
                 const double a_aff = fmin(1.0, amax);
                 sig = (1.0 - a_aff) * (1.0 - a_aff) * (1.0 - a_aff);
@@ -376,7 +478,6 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         for (int k = 0; k < NV; ++k) z[k] = fma(alpha, dz[k], z[k]);
 #pragma unroll 1
         for (int j = 0; j < MR; ++j) {
-            if (!(act >> j & 1u)) continue;
             const int r = lane + 32 * j;
             sv[r] = fma(alpha, av[r], sv[r]);
             lv[r] = fma(alpha, bv[r], lv[r]);
@@ -384,13 +485,9 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         rho *= 1.0 - alpha * cres;
     }
     __syncwarp();
-    if (lane < NV) {
-        // static indexing of z by the owning lane
-#pragma unroll
-        for (int k = 0; k < NV; ++k)
-            if (lane == k) w[W::oZ + k] = z[k];
-    }
     if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) w[W::oZ + k] = z[k];
         w[W::oOut + 0] = obj;
         w[W::oOut + 1] = (double)it;
         // algorithmic flops (2 per FMA): K build m*NV(NV+1), five mat-vec passes 10*m*NV,

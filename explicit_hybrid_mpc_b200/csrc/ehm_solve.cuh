@@ -123,6 +123,11 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
                 act |= 1u << j;
             }
         }
+        if (!(act >> j & 1u)) {  // rows that do not take part: G = 0, h = 1 (ipm_solve contract)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) Gs[k * MRP + r] = 0.0;
+            hs[r] = 1.0;
+        }
     }
     if (__any_sync(kFull, viol)) return out;
     s0 = warp_max(s0);
@@ -292,6 +297,11 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
                 if (!(tau_bits >> j & 1u)) s0 = fmax(s0, -hv * inv);
                 act |= 1u << j;
             }
+        }
+        if (!(act >> j & 1u)) {  // rows that do not take part: G = 0, h = 1 (ipm_solve contract)
+#pragma unroll
+            for (int k = 0; k < NVS; ++k) Gs[k * MRP + r] = 0.0;
+            hs[r] = 1.0;
         }
     }
     if (__any_sync(kFull, viol)) return out;

@@ -301,6 +301,10 @@ def partition_distributed(oracle, roots, group=None, waves_per_round=2, wave=0, 
     rounds = moved = 0
     xch_s = 0.0
     t0 = time.perf_counter()
+    ev0 = ev1 = None
+    if dev.type == 'cuda':
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.default_stream(dev))
     try:
         while True:
             mysize = eng.advance(waves_per_round)
@@ -336,13 +340,18 @@ def partition_distributed(oracle, roots, group=None, waves_per_round=2, wave=0, 
             xch_s += time.perf_counter() - tx
             rounds += 1
             moved += k
+        loop_ms = None
+        if ev0 is not None:
+            ev1.record(torch.cuda.default_stream(dev))
+            ev1.synchronize()
+            loop_ms = ev0.elapsed_time(ev1)   # device clock, idle gaps between rounds included
         arr = eng.fetch(with_origin=True)
         st = eng.stats_dict()
     finally:
         eng.close()
     wall = time.perf_counter() - t0
     info = dict(rank=rank, world=world, wall_s=wall, exchange_s=xch_s, rounds=rounds,
-                records_sent=moved, stats=st)
+                records_sent=moved, stats=st, loop_device_ms=loop_ms)
     result = None
     if gather:
         parts = [None] * world if rank == 0 else None

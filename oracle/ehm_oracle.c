@@ -868,51 +868,61 @@ double ehmo_simplex_volume(int n, const double *R)
 }
 
 /* ------------------------------------------------------------------------------------ */
-/* ECC / L-CSS recursion (lib/worker.py:241-417), serial depth-first per root             */
+/* ECC / L-CSS (lib/worker.py:241-417) driven by a shared LIFO task queue                  */
+/* (lib/scheduler.py:364-599: tasks popped from the tail; every split pushes both children, */
+/* i.e. the reference's "offload the child" path of worker.py:187-239 taken always).        */
+/* The tree does not depend on who processes a node, nor on the order.                      */
 /* ------------------------------------------------------------------------------------ */
+typedef struct task {
+    long id;
+    double *lb;   /* NULL: ECC task; else L-CSS with these inherited bounds (owned) */
+    struct task *next;
+} task;
+
 typedef struct {
     ehmo_problem *pb;
     ehmo_tree t;
-    long cap, max_nodes;
+    long cap;
     int prune;
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    task *top;
+    int busy, nthreads, stop;
 } builder;
 
 static long new_node(builder *b, const double *R, int root_id, int depth)
 {
     ehmo_tree *t = &b->t;
     const int n = t->n, nu = t->nu;
-    if (t->nnodes == b->cap) {
-        long nc = b->cap ? 2 * b->cap : 1024;
-        t->left = (int *)realloc(t->left, nc * sizeof(int));
-        t->right = (int *)realloc(t->right, nc * sizeof(int));
-        t->root_id = (int *)realloc(t->root_id, nc * sizeof(int));
-        t->depth = (int *)realloc(t->depth, nc * sizeof(int));
-        t->cand = (int *)realloc(t->cand, nc * sizeof(int));
-        t->closed = (unsigned char *)realloc(t->closed, nc);
-        t->vertices = (double *)realloc(t->vertices, nc * (n + 1) * n * sizeof(double));
-        t->vcost = (double *)realloc(t->vcost, nc * (n + 1) * sizeof(double));
-        t->vinput = (double *)realloc(t->vinput, nc * (n + 1) * nu * sizeof(double));
-        b->cap = nc;
-    }
-    long id = t->nnodes++;
+    long id = __sync_fetch_and_add(&t->nnodes, 1);
+    if (id >= b->cap) { t->error = 3; __sync_fetch_and_sub(&t->nnodes, 1); return -1; }
     t->left[id] = t->right[id] = -1;
     t->root_id[id] = root_id; t->depth[id] = depth; t->cand[id] = -1; t->closed[id] = 0;
     memcpy(t->vertices + id * (n + 1) * n, R, sizeof(double) * (n + 1) * n);
     memset(t->vcost + id * (n + 1), 0, sizeof(double) * (n + 1));
     memset(t->vinput + id * (n + 1) * nu, 0, sizeof(double) * (n + 1) * nu);
-    if (depth > t->max_depth) t->max_depth = depth;
+    int md;
+    while (depth > (md = t->max_depth) && !__sync_bool_compare_and_swap(&t->max_depth, md, depth)) {}
     return id;
 }
 
-static void lcss(builder *b, long id, double *lb);
+static void push_task(builder *b, long id, double *lb)
+{
+    task *k = (task *)malloc(sizeof(task));
+    k->id = id; k->lb = lb;
+    pthread_mutex_lock(&b->mu);
+    k->next = b->top;
+    b->top = k;
+    pthread_cond_signal(&b->cv);
+    pthread_mutex_unlock(&b->mu);
+}
 
-/* Worker.ecc (lib/worker.py:241-291) */
-static void ecc(builder *b, long id)
+/* Worker.ecc (lib/worker.py:241-291), one node */
+static void ecc_step(builder *b, long id)
 {
     ehmo_problem *pb = b->pb;
     ehmo_tree *t = &b->t;
     const int n = t->n, nu = t->nu;
-    if (t->error || t->nnodes >= b->max_nodes) return;
     double R[MAXNV * MAXNV], Jv[MAXNV], Uv[MAXNV * MAXNV];
     memcpy(R, t->vertices + id * (n + 1) * n, sizeof(double) * (n + 1) * n);
     int c = ehmo_v_r(pb, R, Jv, Uv);
@@ -933,106 +943,109 @@ static void ecc(builder *b, long id)
         ehmo_split(n, R, S1, S2, ij);
         long l = new_node(b, S1, t->root_id[id], t->depth[id] + 1);
         long r = new_node(b, S2, t->root_id[id], t->depth[id] + 1);
+        if (l < 0 || r < 0) return;
         t->left[id] = (int)l; t->right[id] = (int)r;
-        ecc(b, l);
-        ecc(b, r);
+        push_task(b, l, NULL);
+        push_task(b, r, NULL);
     } else {
         t->cand[id] = c;
         memcpy(t->vcost + id * (n + 1), Jv, sizeof(double) * (n + 1));
         memcpy(t->vinput + id * (n + 1) * nu, Uv, sizeof(double) * (n + 1) * nu);
         double *lb = dalloc(pb->ncand);
         for (int k = 0; k < pb->ncand; ++k) lb[k] = -INFINITY;
-        lcss(b, id, lb);
-        free(lb);
+        push_task(b, id, lb);
     }
 }
 
-/* Worker.lcss (lib/worker.py:293-417).  lb: per-candidate bounds of this node (modified in
- * place; children receive copies). */
-static void lcss(builder *b, long id, double *lb)
+/* Worker.lcss (lib/worker.py:293-417), one node; lb is consumed */
+static void lcss_step(builder *b, long id, double *lb)
 {
     ehmo_problem *pb = b->pb;
     ehmo_tree *t = &b->t;
     const int n = t->n, nu = t->nu, nc = pb->ncand;
     double R[MAXNV * MAXNV], Vr[MAXNV], Ur[MAXNV * MAXNV];
-    for (;;) {
-        if (t->error || t->nnodes >= b->max_nodes) break;
-        memcpy(R, t->vertices + id * (n + 1) * n, sizeof(double) * (n + 1) * n);
-        memcpy(Vr, t->vcost + id * (n + 1), sizeof(double) * (n + 1));
-        memcpy(Ur, t->vinput + id * (n + 1) * nu, sizeof(double) * (n + 1) * nu);
-        int cref = t->cand[id];
-        double th[MAXNV], Jn[MAXNV], Un[MAXNV * MAXNV];
-        ehmo_lcss_result res;
-        ehmo_lcss_eval(pb, R, Vr, cref, lb, b->prune, th, Jn, Un, &res);
-        t->nfail += res.n_fail;
-        if (getenv("EHMO_TRACE"))
-            fprintf(stderr, "node %ld depth %d cref %d evaluated %d tref %.4g conv %d cstar %d vs %d\n",
-                    id, t->depth[id], cref, res.n_eval, res.t_ref, res.converged, res.cstar, res.var_small);
-        if (res.converged) { /* worker.py:368-375 close leaf */
-            t->closed[id] = 1;
-            t->nleaves++;
-            break;
-        }
-        int cnew = cref;
-        if (res.cstar >= 0) { /* worker.py:389-395 */
-            cnew = res.cstar;
-            ehmo_lb_rebase(n, nc, Vr, Jn, lb);
-            lb[cref] = -INFINITY; /* the old commutation becomes an ordinary candidate */
-            memcpy(Vr, Jn, sizeof(double) * (n + 1));
-            memcpy(Ur, Un, sizeof(double) * (n + 1) * nu);
-        }
-        if (res.cstar >= 0 && res.var_small) { /* worker.py:396-401: swap, same node */
-            t->cand[id] = cnew;
-            memcpy(t->vcost + id * (n + 1), Vr, sizeof(double) * (n + 1));
-            memcpy(t->vinput + id * (n + 1) * nu, Ur, sizeof(double) * (n + 1) * nu);
-            continue;
-        }
-        /* worker.py:403-417: split, re-solve only the midpoint vertex */
-        double S1[MAXNV * MAXNV], S2[MAXNV * MAXNV], Jm, Um[MAXNV];
-        int ij[2];
-        ehmo_split(n, R, S1, S2, ij);
-        if (ehmo_p_theta_delta(pb, S1 + ij[0] * n, cnew, &Jm, Um) != 1) {
-            t->error = 2; /* cannot happen for a convex feasible set; reference would raise */
-            break;
-        }
-        long l = new_node(b, S1, t->root_id[id], t->depth[id] + 1);
-        long r = new_node(b, S2, t->root_id[id], t->depth[id] + 1);
-        t->left[id] = (int)l; t->right[id] = (int)r;
-        for (int side = 0; side < 2; ++side) {
-            long ch = side ? r : l;
-            t->cand[ch] = cnew;
-            memcpy(t->vcost + ch * (n + 1), Vr, sizeof(double) * (n + 1));
-            memcpy(t->vinput + ch * (n + 1) * nu, Ur, sizeof(double) * (n + 1) * nu);
-            t->vcost[ch * (n + 1) + ij[side]] = Jm;
-            memcpy(t->vinput + (ch * (n + 1) + ij[side]) * nu, Um, sizeof(double) * nu);
-        }
-        double *ll = dcopy(lb, nc);
-        lcss(b, l, ll);
-        free(ll);
-        lcss(b, r, lb);
-        break;
+    memcpy(R, t->vertices + id * (n + 1) * n, sizeof(double) * (n + 1) * n);
+    memcpy(Vr, t->vcost + id * (n + 1), sizeof(double) * (n + 1));
+    memcpy(Ur, t->vinput + id * (n + 1) * nu, sizeof(double) * (n + 1) * nu);
+    int cref = t->cand[id];
+    double th[MAXNV], Jn[MAXNV], Un[MAXNV * MAXNV];
+    ehmo_lcss_result res;
+    ehmo_lcss_eval(pb, R, Vr, cref, lb, b->prune, th, Jn, Un, &res);
+    __sync_fetch_and_add(&t->nfail, res.n_fail);
+    if (getenv("EHMO_TRACE"))
+        fprintf(stderr, "node %ld depth %d cref %d evaluated %d tref %.4g conv %d cstar %d vs %d\n",
+                id, t->depth[id], cref, res.n_eval, res.t_ref, res.converged, res.cstar, res.var_small);
+    if (res.converged) { /* worker.py:368-375 close leaf */
+        t->closed[id] = 1;
+        __sync_fetch_and_add(&t->nleaves, 1);
+        free(lb);
+        return;
     }
+    int cnew = cref;
+    if (res.cstar >= 0) { /* worker.py:389-395 */
+        cnew = res.cstar;
+        ehmo_lb_rebase(n, nc, Vr, Jn, lb);
+        lb[cref] = -INFINITY; /* the old commutation becomes an ordinary candidate */
+        memcpy(Vr, Jn, sizeof(double) * (n + 1));
+        memcpy(Ur, Un, sizeof(double) * (n + 1) * nu);
+    }
+    if (res.cstar >= 0 && res.var_small) { /* worker.py:396-401: swap, same node again */
+        t->cand[id] = cnew;
+        memcpy(t->vcost + id * (n + 1), Vr, sizeof(double) * (n + 1));
+        memcpy(t->vinput + id * (n + 1) * nu, Ur, sizeof(double) * (n + 1) * nu);
+        push_task(b, id, lb);
+        return;
+    }
+    /* worker.py:403-417: split, re-solve only the midpoint vertex */
+    double S1[MAXNV * MAXNV], S2[MAXNV * MAXNV], Jm, Um[MAXNV];
+    int ij[2];
+    ehmo_split(n, R, S1, S2, ij);
+    if (ehmo_p_theta_delta(pb, S1 + ij[0] * n, cnew, &Jm, Um) != 1) {
+        t->error = 2; /* cannot happen for a convex feasible set; the reference would raise */
+        free(lb);
+        return;
+    }
+    long l = new_node(b, S1, t->root_id[id], t->depth[id] + 1);
+    long r = new_node(b, S2, t->root_id[id], t->depth[id] + 1);
+    if (l < 0 || r < 0) { free(lb); return; }
+    t->left[id] = (int)l; t->right[id] = (int)r;
+    for (int side = 0; side < 2; ++side) {
+        long ch = side ? r : l;
+        t->cand[ch] = cnew;
+        memcpy(t->vcost + ch * (n + 1), Vr, sizeof(double) * (n + 1));
+        memcpy(t->vinput + ch * (n + 1) * nu, Ur, sizeof(double) * (n + 1) * nu);
+        t->vcost[ch * (n + 1) + ij[side]] = Jm;
+        memcpy(t->vinput + (ch * (n + 1) + ij[side]) * nu, Um, sizeof(double) * nu);
+    }
+    push_task(b, l, dcopy(lb, nc));
+    push_task(b, r, lb);
 }
-
-typedef struct {
-    ehmo_problem *pb;
-    int nroots;
-    const double *roots;
-    int *next;
-    long max_nodes;
-    builder b;
-    int *root_of; /* unused */
-} thread_arg;
 
 static void *thread_main(void *p)
 {
-    thread_arg *a = (thread_arg *)p;
-    const int n = a->pb->n;
+    builder *b = (builder *)p;
     for (;;) {
-        int r = __sync_fetch_and_add(a->next, 1);
-        if (r >= a->nroots) break;
-        long id = new_node(&a->b, a->roots + (size_t)r * (n + 1) * n, r, 0);
-        ecc(&a->b, id);
+        pthread_mutex_lock(&b->mu);
+        while (!b->top && b->busy > 0 && !b->stop) pthread_cond_wait(&b->cv, &b->mu);
+        if (b->stop || (!b->top && b->busy == 0)) {
+            pthread_cond_broadcast(&b->cv);
+            pthread_mutex_unlock(&b->mu);
+            break;
+        }
+        task *k = b->top;
+        b->top = k->next;
+        b->busy++;
+        pthread_mutex_unlock(&b->mu);
+        if (!b->t.error) {
+            if (k->lb) lcss_step(b, k->id, k->lb);
+            else ecc_step(b, k->id);
+        } else free(k->lb);
+        free(k);
+        pthread_mutex_lock(&b->mu);
+        b->busy--;
+        if (b->t.error) b->stop = 1;
+        if ((!b->top && b->busy == 0) || b->stop) pthread_cond_broadcast(&b->cv);
+        pthread_mutex_unlock(&b->mu);
     }
     return NULL;
 }
@@ -1041,56 +1054,37 @@ ehmo_tree *ehmo_partition(ehmo_problem *pb, int nroots, const double *roots, int
                           long max_nodes, int prune)
 {
     if (nthreads < 1) nthreads = 1;
-    if (nthreads > nroots) nthreads = nroots;
-    if (max_nodes <= 0) max_nodes = 1L << 40;
-    int next = 0;
-    long solves0 = pb->nsolves;
-    thread_arg *args = (thread_arg *)calloc(nthreads, sizeof(thread_arg));
-    pthread_t *th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
-    for (int i = 0; i < nthreads; ++i) {
-        args[i].pb = pb; args[i].nroots = nroots; args[i].roots = roots; args[i].next = &next;
-        args[i].b.pb = pb; args[i].b.max_nodes = max_nodes; args[i].b.prune = prune;
-        args[i].b.t.n = pb->n; args[i].b.t.nu = pb->nu;
-        pthread_create(&th[i], NULL, thread_main, &args[i]);
-    }
-    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
-    /* merge per-thread trees */
-    ehmo_tree *t = (ehmo_tree *)calloc(1, sizeof(ehmo_tree));
     const int n = pb->n, nu = pb->nu;
+    builder b;
+    memset(&b, 0, sizeof b);
+    b.pb = pb; b.prune = prune; b.nthreads = nthreads;
+    b.cap = max_nodes > 0 ? max_nodes : (1L << 21);
+    pthread_mutex_init(&b.mu, NULL);
+    pthread_cond_init(&b.cv, NULL);
+    ehmo_tree *t = &b.t;
     t->n = n; t->nu = nu;
-    long total = 0;
-    for (int i = 0; i < nthreads; ++i) total += args[i].b.t.nnodes;
-    t->left = (int *)malloc(total * sizeof(int)); t->right = (int *)malloc(total * sizeof(int));
-    t->root_id = (int *)malloc(total * sizeof(int)); t->depth = (int *)malloc(total * sizeof(int));
-    t->cand = (int *)malloc(total * sizeof(int)); t->closed = (unsigned char *)malloc(total ? total : 1);
-    t->vertices = dalloc(total * (n + 1) * n); t->vcost = dalloc(total * (n + 1));
-    t->vinput = dalloc(total * (n + 1) * nu);
-    long off = 0;
-    for (int i = 0; i < nthreads; ++i) {
-        ehmo_tree *s = &args[i].b.t;
-        for (long k = 0; k < s->nnodes; ++k) {
-            t->left[off + k] = s->left[k] < 0 ? -1 : (int)(s->left[k] + off);
-            t->right[off + k] = s->right[k] < 0 ? -1 : (int)(s->right[k] + off);
-            t->root_id[off + k] = s->root_id[k]; t->depth[off + k] = s->depth[k];
-            t->cand[off + k] = s->cand[k]; t->closed[off + k] = s->closed[k];
-        }
-        if (s->nnodes) {
-            memcpy(t->vertices + off * (n + 1) * n, s->vertices, s->nnodes * (n + 1) * n * sizeof(double));
-            memcpy(t->vcost + off * (n + 1), s->vcost, s->nnodes * (n + 1) * sizeof(double));
-            memcpy(t->vinput + off * (n + 1) * nu, s->vinput, s->nnodes * (n + 1) * nu * sizeof(double));
-        }
-        off += s->nnodes;
-        t->nleaves += s->nleaves;
-        if (s->max_depth > t->max_depth) t->max_depth = s->max_depth;
-        if (s->error) t->error = s->error;
-        t->nfail += s->nfail;
-        free(s->left); free(s->right); free(s->root_id); free(s->depth); free(s->cand);
-        free(s->closed); free(s->vertices); free(s->vcost); free(s->vinput);
+    t->left = (int *)malloc(b.cap * sizeof(int)); t->right = (int *)malloc(b.cap * sizeof(int));
+    t->root_id = (int *)malloc(b.cap * sizeof(int)); t->depth = (int *)malloc(b.cap * sizeof(int));
+    t->cand = (int *)malloc(b.cap * sizeof(int)); t->closed = (unsigned char *)malloc(b.cap);
+    t->vertices = (double *)malloc(b.cap * (n + 1) * n * sizeof(double));
+    t->vcost = (double *)malloc(b.cap * (n + 1) * sizeof(double));
+    t->vinput = (double *)malloc(b.cap * (n + 1) * nu * sizeof(double));
+    long solves0 = pb->nsolves;
+    for (int r = nroots - 1; r >= 0; --r) { /* reverse: root 0 is popped first */
+        long id = new_node(&b, roots + (size_t)r * (n + 1) * n, r, 0);
+        push_task(&b, id, NULL);
     }
-    t->nnodes = total;
-    t->nsolves = pb->nsolves - solves0;
-    free(args); free(th);
-    return t;
+    pthread_t *th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
+    for (int i = 0; i < nthreads; ++i) pthread_create(&th[i], NULL, thread_main, &b);
+    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
+    free(th);
+    while (b.top) { task *k = b.top; b.top = k->next; free(k->lb); free(k); }
+    pthread_mutex_destroy(&b.mu);
+    pthread_cond_destroy(&b.cv);
+    ehmo_tree *out = (ehmo_tree *)malloc(sizeof(ehmo_tree));
+    *out = *t;
+    out->nsolves = pb->nsolves - solves0;
+    return out;
 }
 
 void ehmo_tree_free(ehmo_tree *t)

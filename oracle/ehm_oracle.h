@@ -88,7 +88,8 @@ int ehmo_min_over_simplex(ehmo_problem *pb, const double *R, int cand, double *v
 void ehmo_split(int n, const double *R, double *S1, double *S2, int *ij);
 double ehmo_simplex_volume(int n, const double *R);
 
-/* Whole-tree partition (serial DFS per root; roots distributed over nthreads).
+/* Whole-tree partition: nthreads workers over one shared LIFO task queue (every node visit is
+ * a task, as in the reference's scheduler/worker farm).
  * roots: nroots x (n+1) x n.  Output node arrays are allocated by the library and returned
  * through ehmo_tree; free with ehmo_tree_free. */
 typedef struct {
