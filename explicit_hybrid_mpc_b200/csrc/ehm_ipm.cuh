@@ -36,6 +36,10 @@ namespace ehm {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// debugging aid: per-iteration trace of the LAST solve that ran with tracing enabled
+__device__ double g_trace[8 * 128];
+__device__ int g_trace_on = 0;
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -246,6 +250,8 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
             const double l = 1.0 / s;
             sv[r] = s;
             lv[r] = l;
+            av[r] = l;
+            bv[r] = 0.0;
 #pragma unroll
             for (int k = 0; k < NV; ++k) gl[k] = fma(g[k], l, gl[k]);
         }
@@ -274,7 +280,10 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         for (int j = 0; j < MR; j += 2) {
             const bool on1 = (j + 1 < MR);
             const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
-            const double m1 = on1 ? 1.0 : 0.0;
+            // rows that do not take part in THIS solve (e.g. the epigraph rows during phase 1)
+            // may hold data: mask them (their s = 1, lam = 0 already keep K and the gap clean)
+            const double m0 = (act >> j & 1u) ? 1.0 : 0.0;
+            const double m1 = (on1 && (act >> (j + 1) & 1u)) ? 1.0 : 0.0;
             double g0[NV], g1[NV], gz0 = 0.0, gz1 = 0.0;
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
@@ -283,11 +292,11 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                 gz0 = fma(g0[k], z[k], gz0);
                 gz1 = fma(g1[k], z[k], gz1);
             }
-            const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0], l1 = lv[r1] * m1;
+            const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0] * m0, l1 = lv[r1] * m1;
             const double rs0 = 1.0 / s0, rs1 = 1.0 / s1;
             av[r0] = rs0;
             if (on1) av[r1] = rs1;
-            rpm = fmax(rpm, fmax(fabs(gz0 + s0 - hs[r0]), m1 * fabs(gz1 + s1 - hs[r1])));
+            rpm = fmax(rpm, fmax(m0 * fabs(gz0 + s0 - hs[r0]), m1 * fabs(gz1 + s1 - hs[r1])));
             mu = fma(s0, l0, fma(s1, l1, mu));
             lmx = fmax(lmx, fmax(l0, l1));
             const double wt0 = l0 * rs0, wt1 = l1 * rs1;
@@ -331,12 +340,17 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                 break;
             }
         }
+        if (g_trace_on && lane == 0 && it < 120) {
+            g_trace[8 * it + 0] = it; g_trace[8 * it + 1] = rpm; g_trace[8 * it + 2] = mu;
+            g_trace[8 * it + 3] = obj; g_trace[8 * it + 4] = rho * rd0; g_trace[8 * it + 5] = lmx;
+            g_trace[8 * it + 6] = mact; g_trace[8 * it + 7] = NV;
+        }
         if (it == EHM_MAX_ITER) break;
         const double mu_mean = mu / mact;
         // ---- K -> packed scratch -> lane-parallel Cholesky (rows in registers, pivot rows
-        //      broadcast by shuffle) -> factor replicated into every lane --------------------
+        //      broadcast by shuffle) -> packed factor in shared memory (read by broadcast) -----
         reduce_chunks<PK / 8>(acc, red, NK, scr, lane);
-        double L[NK], inv[NV];
+        double inv[NV];
         {
             double Lr[NV], d0 = 1.0;
             const int li = lane < NV ? lane : 0;
@@ -364,16 +378,12 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                 break;
             }
             __syncwarp();
-#pragma unroll
-            for (int k = 0; k < NK; ++k) L[k] = Ls[k];
-            __syncwarp();
         }
         // ---- predictor (trip 0) and corrector (trip 1) share one code path -------------------
         double sig = 0.0, cres = 1.0, alpha = 1.0;
         double dz[NV];
 #pragma unroll 1
         for (int trip = 0; trip < 2; ++trip) {
-            const double tsel = trip ? 1.0 : 0.0;
             double rh[PV];
 #pragma unroll
             for (int k = 0; k < PV; ++k) rh[k] = 0.0;
@@ -394,14 +404,14 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                 const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0], l1 = lv[r1];
                 const double rp0 = gz0 + s0 - hs[r0], rp1 = gz1 + s1 - hs[r1];
                 // rc: s.lam (predictor) or s.lam + ds_aff.dl_aff - sigma mu (corrector)
-                const double rc0 = m0 * fma(tsel, bv[r0] - sig * mu_mean, s0 * l0);
-                const double rc1 = m1 * fma(tsel, bv[r1] - sig * mu_mean, s1 * l1);
+                const double rc0 = m0 * (s0 * l0 + (trip ? bv[r0] - sig * mu_mean : 0.0));
+                const double rc1 = m1 * (s1 * l1 + (trip ? bv[r1] - sig * mu_mean : 0.0));
                 if (trip) {
                     bv[r0] = rc0;
                     if (on1) bv[r1] = rc1;
                 }
                 // rhs = -c (Hz+f) - G'(c lam + t),  t = (lam c rp - rc)/s
-                const double q0 = fma(cres, l0, (l0 * cres * rp0 - rc0) * av[r0]);
+                const double q0 = m0 * fma(cres, l0, (l0 * cres * rp0 - rc0) * av[r0]);
                 const double q1 = m1 * fma(cres, l1, (l1 * cres * rp1 - rc1) * av[r1]);
 #pragma unroll
                 for (int k = 0; k < NV; ++k) rh[k] = fma(g0[k], q0, fma(g1[k], q1, rh[k]));
@@ -415,13 +425,13 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
             for (int k = 0; k < NV; ++k) {
                 dz[k] *= inv[k];
 #pragma unroll
-                for (int i = k + 1; i < NV; ++i) dz[i] = fma(-L[tri(i, k)], dz[k], dz[i]);
+                for (int i = k + 1; i < NV; ++i) dz[i] = fma(-Ls[tri(i, k)], dz[k], dz[i]);
             }
 #pragma unroll
             for (int k = NV - 1; k >= 0; --k) {
                 dz[k] *= inv[k];
 #pragma unroll
-                for (int i = 0; i < k; ++i) dz[i] = fma(-L[tri(k, i)], dz[k], dz[i]);
+                for (int i = 0; i < k; ++i) dz[i] = fma(-Ls[tri(k, i)], dz[k], dz[i]);
             }
             // step to the boundary: min over rows of s/(-ds) and lam/(-dl), as fractions
             double an = 1.0, ad = 1e-300;   // num/den = "infinite" step

@@ -14,16 +14,16 @@ std::atomic<int64_t> g_launches{0};
 using namespace ehm;
 
 // ---------------------------------------------------------------------------------------
-// compiled problem shapes <U, NX, MR>: U = N*n_u inputs, NX = n, MR = ceil(rows/32) where
+// compiled problem shapes <U, NX, MRI, MRC>: U = N*n_u inputs, NX = n, MR = ceil(rows/32) where
 // rows = N*p + n + 3 (stage rows + simplex rows + two epigraph rows)
 // ---------------------------------------------------------------------------------------
-#define EHM_FOR_EACH_CFG(X) X(0, 5, 4, 7) /* inverted pendulum, N=5 */
+#define EHM_FOR_EACH_CFG(X) X(0, 5, 4, 7, 3) /* inverted pendulum, N=5: 217 rows in, <= 96 after pre-solve */
 
 static int find_cfg(int U, int NX, int rows_total)
 {
     const int MR = (rows_total + 31) / 32;
-#define X(ID, UU, NN, MM) \
-    if (U == UU && NX == NN && MR == MM) return ID;
+#define X(ID, UU, NN, MM, CC) \
+    if (U == UU && NX == NN && MR == MM) return ID + 0 * CC;
     EHM_FOR_EACH_CFG(X)
 #undef X
     return -1;
@@ -32,8 +32,8 @@ static int find_cfg(int U, int NX, int rows_total)
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
-constexpr int kWarpsPerCta = 1;   // one problem per CTA-warp; 7 CTAs (28.5 KB each) per SM
-constexpr int kCtasPerSm = 7;
+constexpr int kWarpsPerCta = 1;   // one problem per one-warp CTA
+constexpr int kCtasPerSm = 11;    // 18.7 KB of shared memory and <= 184 registers per warp
 
 __device__ __forceinline__ long long next_item(DevCounters *cnt, int lane)
 {
@@ -52,21 +52,21 @@ __device__ __forceinline__ void account(DevCounters *cnt, const SolveOut &o, int
     }
 }
 
-template <int U, int NX, int MR>
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+template <int U, int NX, int MRI, int MRC>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
 k_point_batch(DevTables tb, int B, const double *__restrict__ theta, const int *__restrict__ cand,
               double *J, double *u0, int *status, DevCounters *cnt)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MR>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
     for (;;) {
         const long long b = next_item(cnt, lane);
         if (b >= B) break;
         const int c = cand[b];
         SolveOut o{0, 0.0, 0, 0, 0.0};
         if (c >= 0 && c < tb.ncand)
-            o = solve_point<U, NX, MR>(tb, c, theta + (size_t)b * NX, ws, u0 ? u0 + (size_t)b * tb.nu : nullptr, lane);
+            o = solve_point<U, NX, MRI, MRC>(tb, c, theta + (size_t)b * NX, ws, u0 ? u0 + (size_t)b * tb.nu : nullptr, lane);
         account(cnt, o, lane);
         if (lane == 0) {
             status[b] = o.status;
@@ -76,22 +76,22 @@ k_point_batch(DevTables tb, int B, const double *__restrict__ theta, const int *
     }
 }
 
-template <int U, int NX, int MR>
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+template <int U, int NX, int MRI, int MRC>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
 k_simplex_batch(DevTables tb, int B, const double *__restrict__ R, const double *__restrict__ Vr,
                 const int *__restrict__ cand, int mode, int with_phase1, double *val, double *sol,
                 int *status, DevCounters *cnt)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MR>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
     for (;;) {
         const long long b = next_item(cnt, lane);
         if (b >= B) break;
         const int c = cand[b];
         SolveOut o{0, 0.0, 0, 0, 0.0};
         if (c >= 0 && c < tb.ncand)
-            o = solve_simplex<U, NX, MR>(tb, c, R + (size_t)b * (NX + 1) * NX,
+            o = solve_simplex<U, NX, MRI, MRC>(tb, c, R + (size_t)b * (NX + 1) * NX,
                                          Vr ? Vr + (size_t)b * (NX + 1) : nullptr, mode,
                                          with_phase1 != 0, ws,
                                          sol ? sol + (size_t)b * (NX + 1) : nullptr, lane);
@@ -324,10 +324,10 @@ extern "C" int ehm_qp_theta_delta_batch(ehm_problem *p, int B, const double *d_t
     cudaStream_t st = (cudaStream_t)stream;
     EHM_CUDA(cudaMemsetAsync(&p->dcnt->work, 0, sizeof(unsigned long long), st));
     switch (p->cfg) {
-#define X(ID, UU, NN, MM)                                                                     \
+#define X(ID, UU, NN, MM, CC)                                                                     \
     case ID: {                                                                                \
-        auto kern = k_point_batch<UU, NN, MM>;                                                \
-        const size_t sm = (size_t)kWarpsPerCta * WarpWs<UU, NN, MM>::kDoubles * sizeof(double); \
+        auto kern = k_point_batch<UU, NN, MM, CC>;                                                \
+        const size_t sm = (size_t)kWarpsPerCta * WarpWs<UU, NN, MM, CC>::kDoubles * sizeof(double); \
         int rc = set_smem(kern, sm);                                                          \
         if (rc) return rc;                                                                    \
         kern<<<grid_for(p, B), 32 * kWarpsPerCta, sm, st>>>(p->tb, B, d_theta, d_cand, d_J, d_u0, \
@@ -353,10 +353,10 @@ extern "C" int ehm_simplex_batch(ehm_problem *p, int B, const double *d_R, const
     cudaStream_t st = (cudaStream_t)stream;
     EHM_CUDA(cudaMemsetAsync(&p->dcnt->work, 0, sizeof(unsigned long long), st));
     switch (p->cfg) {
-#define X(ID, UU, NN, MM)                                                                     \
+#define X(ID, UU, NN, MM, CC)                                                                     \
     case ID: {                                                                                \
-        auto kern = k_simplex_batch<UU, NN, MM>;                                              \
-        const size_t sm = (size_t)kWarpsPerCta * WarpWs<UU, NN, MM>::kDoubles * sizeof(double); \
+        auto kern = k_simplex_batch<UU, NN, MM, CC>;                                              \
+        const size_t sm = (size_t)kWarpsPerCta * WarpWs<UU, NN, MM, CC>::kDoubles * sizeof(double); \
         int rc = set_smem(kern, sm);                                                          \
         if (rc) return rc;                                                                    \
         kern<<<grid_for(p, B), 32 * kWarpsPerCta, sm, st>>>(p->tb, B, d_R, d_Vr, d_cand, mode, \
@@ -450,18 +450,18 @@ void fill_stats(ehm_partition *t, ehm_partition_stats *stats)
     stats->stage_flops[5] = c1.flops[3] - c0.flops[3]; stats->stage_flops[7] = c1.flops[4] - c0.flops[4];
 }
 
-template <int U, int NX, int MR>
+template <int U, int NX, int MRI, int MRC>
 int advance_t(ehm_partition *t, int64_t max_waves)
 {
     ehm_problem *p = t->pb;
     const DevTables &tb = p->tb;
     const ehm_partition_opts &o = t->opts;
     const int ncand = tb.ncand;
-    const size_t smem = (size_t)kWarpsPerCta * WarpWs<U, NX, MR>::kDoubles * sizeof(double);
-    auto kref = k_lcss_ref<U, NX, MR>;
-    auto keval = k_lcss_eval<U, NX, MR>;
-    auto kpts = k_lcss_points<U, NX, MR>;
-    auto kecc = k_ecc_points<U, NX, MR>;
+    const size_t smem = (size_t)kWarpsPerCta * WarpWs<U, NX, MRI, MRC>::kDoubles * sizeof(double);
+    auto kref = k_lcss_ref<U, NX, MRI, MRC>;
+    auto keval = k_lcss_eval<U, NX, MRI, MRC>;
+    auto kpts = k_lcss_points<U, NX, MRI, MRC>;
+    auto kecc = k_ecc_points<U, NX, MRI, MRC>;
     int rc;
     if ((rc = set_smem(kref, smem)) || (rc = set_smem(keval, smem)) || (rc = set_smem(kpts, smem)) ||
         (rc = set_smem(kecc, smem)))
@@ -645,8 +645,8 @@ extern "C" int ehm_partition_advance(ehm_partition *t, int64_t max_waves, ehm_pa
     if (!t) return fail(EHM_EINVAL, "null partition");
     int rc;
     switch (t->pb->cfg) {
-#define X(ID, UU, NN, MM) \
-    case ID: rc = advance_t<UU, NN, MM>(t, max_waves); break;
+#define X(ID, UU, NN, MM, CC) \
+    case ID: rc = advance_t<UU, NN, MM, CC>(t, max_waves); break;
         EHM_FOR_EACH_CFG(X)
 #undef X
     default: rc = fail(EHM_EINVAL, "no kernel for this problem shape");
@@ -878,5 +878,21 @@ extern "C" int ehm_hbm_peak(int64_t bytes, double *gbs)
     cudaFree(b);
     EHM_CUDA(cudaGetLastError());
     *gbs = best;
+    return EHM_OK;
+}
+
+// ---- debugging aid -----------------------------------------------------------------------
+extern "C" int ehm_debug_trace(int on)
+{
+    EHM_CUDA(cudaMemcpyToSymbol(g_trace_on, &on, sizeof(int)));
+    if (on) {
+        static double zeros[8 * 128];
+        EHM_CUDA(cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros)));
+    }
+    return EHM_OK;
+}
+extern "C" int ehm_debug_fetch(double *out)
+{
+    EHM_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(double) * 8 * 128));
     return EHM_OK;
 }

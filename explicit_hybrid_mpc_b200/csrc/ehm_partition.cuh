@@ -152,18 +152,18 @@ __global__ void k_pop(Frontier fr, WaveBuf wv, int base, int W, int ncand, Ctl *
 // ------------------------------------------------------------------------------------------
 // k_lcss_ref: t*_ref (no phase 1: delta_ref is feasible at every vertex)
 // ------------------------------------------------------------------------------------------
-template <int U, int NX, int MR>
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+template <int U, int NX, int MRI, int MRC>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
 k_lcss_ref(DevTables tb, NodeStore ns, WaveBuf wv, int W, Ctl *ctl, DevCounters *cnt)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MR>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
     for (;;) {
         const long long e = grab(&ctl->cur[0], lane);
         if (e >= W) break;
         const int nd = wv.node[e];
-        const SolveOut o = solve_simplex<U, NX, MR>(tb, ns.cand[nd], ns.verts + (size_t)nd * (NX + 1) * NX,
+        const SolveOut o = solve_simplex<U, NX, MRI, MRC>(tb, ns.cand[nd], ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, false,
                                                     ws, nullptr, lane);
         account(cnt, o, lane, 1);
@@ -210,20 +210,20 @@ __global__ void k_lcss_items(NodeStore ns, WaveBuf wv, int W, int ncand, Ctl *ct
 // ------------------------------------------------------------------------------------------
 // k_lcss_eval: alive test + epigraph QP per item
 // ------------------------------------------------------------------------------------------
-template <int U, int NX, int MR>
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+template <int U, int NX, int MRI, int MRC>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
 k_lcss_eval(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MR>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
     const int nitems = ctl->nitems;
     for (;;) {
         const long long it = grab(&ctl->cur[1], lane);
         if (it >= nitems) break;
         const int2 ec = wv.items[it];
         const int nd = wv.node[ec.x];
-        const SolveOut o = solve_simplex<U, NX, MR>(tb, ec.y, ns.verts + (size_t)nd * (NX + 1) * NX,
+        const SolveOut o = solve_simplex<U, NX, MRI, MRC>(tb, ec.y, ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, true, ws,
                                                     wv.it_sol + (size_t)it * (NX + 1), lane);
         account(cnt, o, lane, 2);
@@ -330,13 +330,13 @@ __global__ void k_lcss_select(NodeStore ns, WaveBuf wv, int W, int ncand, Ctl *c
 // ------------------------------------------------------------------------------------------
 // k_lcss_points: vertex / midpoint P_theta_delta and min-over-simplex problems
 // ------------------------------------------------------------------------------------------
-template <int U, int NX, int MR>
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+template <int U, int NX, int MRI, int MRC>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
 k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MR>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
     const int np = ctl->npitems;
     for (;;) {
         const long long q = grab(&ctl->cur[2], lane);
@@ -345,7 +345,7 @@ k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt
         const int nd = wv.node[pi.e];
         SolveOut o;
         if (pi.i < 0) {
-            o = solve_simplex<U, NX, MR>(tb, pi.c, ns.verts + (size_t)nd * (NX + 1) * NX, nullptr,
+            o = solve_simplex<U, NX, MRI, MRC>(tb, pi.c, ns.verts + (size_t)nd * (NX + 1) * NX, nullptr,
                                          EHM_SX_MINV, false, ws, nullptr, lane);
             if (lane == 0) {
                 wv.minv[pi.e] = o.val;
@@ -355,7 +355,7 @@ k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt
             const double *th = (pi.i <= NX) ? ns.verts + ((size_t)nd * (NX + 1) + pi.i) * NX
                                             : wv.vmid + (size_t)pi.e * NX;
             const size_t slot = ((size_t)pi.e * (kSelT + 1) + pi.k) * (NX + 2) + pi.i;
-            o = solve_point<U, NX, MR>(tb, pi.c, th, ws, wv.ptU + slot * tb.nu, lane);
+            o = solve_point<U, NX, MRI, MRC>(tb, pi.c, th, ws, wv.ptU + slot * tb.nu, lane);
             if (lane == 0) {
                 wv.ptJ[slot] = o.val;
                 wv.ptS[slot] = o.status;
@@ -526,13 +526,13 @@ __global__ void k_lcss_final(DevTables tb, NodeStore ns, Frontier fr, WaveBuf wv
 // ------------------------------------------------------------------------------------------
 // ECC (lib/worker.py:241-291): V_R over all candidates, canonical argmin of summed costs
 // ------------------------------------------------------------------------------------------
-template <int U, int NX, int MR>
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+template <int U, int NX, int MRI, int MRC>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
 k_ecc_points(DevTables tb, NodeStore ns, EccBuf eb, int q0, int ne, int centroid, Ctl *ctl, DevCounters *cnt)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MR>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
     const int ncand = tb.ncand;
     const long long per = centroid ? ncand : (long long)ncand * (NX + 1);
     const long long total = per * ne;
@@ -558,13 +558,13 @@ k_ecc_points(DevTables tb, NodeStore ns, EccBuf eb, int q0, int ne, int centroid
         }
         // theta must live in global/shared memory for solve_point: stage it in the warp's
         // reduction scratch
-        double *thp = ws + WarpWs<U, NX, MR>::oV;
+        double *thp = ws + WarpWs<U, NX, MRI, MRC>::oV;
         if (lane == 0)
             for (int k = 0; k < NX; ++k) thp[k] = th[k];
         __syncwarp();
         const size_t slot = ((size_t)e * ncand + c) * (NX + 2) + i;
         double *up = (i <= NX) ? eb.U + (((size_t)e * ncand + c) * (NX + 1) + i) * tb.nu : nullptr;
-        const SolveOut o = solve_point<U, NX, MR>(tb, c, thp, ws, up, lane);
+        const SolveOut o = solve_point<U, NX, MRI, MRC>(tb, c, thp, ws, up, lane);
         account(cnt, o, lane, 4);
         if (lane == 0) {
             eb.J[slot] = o.val;

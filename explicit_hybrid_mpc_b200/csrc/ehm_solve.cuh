@@ -10,14 +10,26 @@
 // Every problem class runs through ONE instantiation of ipm_solve (point problems NV=U+1,
 // simplex problems NV=U+NX+1): the phase-1 variable sigma, the epigraph variable tau and --
 // where a problem has one variable less -- an inert dummy column (zero coefficients, zero
-// cost; its Cholesky pivot is frozen by the guard) share the last column.  That keeps the hot
-// code of a kernel inside the instruction cache.
+// cost; its Cholesky pivot is frozen by the guard) share the last column.
+//
+// Row pre-solve.  The condensed problems carry every big-M row of the reference
+// (lib/mpc_library.py:529-534): 210 rows for the pendulum, of which ~160 can never bind inside
+// the box |uhat| <= 1 the input-bound rows impose.  A normalised row a'z <= h is dropped when
+//      sup_{|u|<=1, beta in simplex} a'z  =  |a_u|_1 + max(0, max_i a_beta_i)  <=  h - TAU_DROP,
+// which is exact for every decision the engine takes (a point that satisfies the kept rows,
+// which include the box rows, with margin TAU_INT satisfies the dropped ones with margin
+// TAU_DROP > TAU_INT; optima are unchanged because the feasible set is).  The surviving rows
+// (34-61 for the pendulum) are compacted with warp ballots, so the solver works on <= 96 rows
+// (MRC = 3 per lane) instead of 224: 3-4x less work per iteration and a 16 KB instead of 31 KB
+// shared-memory tile, i.e. 12 instead of 7 resident warps per SM.
 //
 // Candidate tables live in global memory (L2 resident: 60 MB for the pendulum), column-major
 // with the row index fastest so that a warp's load of one column is one coalesced 256 B
 // segment per 32 rows.
 #pragma once
 #include "ehm_ipm.cuh"
+
+#define EHM_TAU_DROP 1e-3
 
 namespace ehm {
 
@@ -32,26 +44,24 @@ struct DevTables {
     double eps_a, eps_r;
 };
 
-// Shared-memory workspace of one warp: the solver block of the widest problem; the assembly
-// scratch (cost transform, simplex geometry) aliases the per-row state vectors, which are
-// only live inside ipm_solve.
-template <int U, int NX, int MR>
+// Shared-memory workspace of one warp.  MRI = input row slots per lane (ceil(rows/32) of the
+// un-presolved problem), MRC = row capacity per lane after the pre-solve.
+template <int U, int NX, int MRI, int MRC>
 struct WarpWs {
     static constexpr int NVS = U + NX + 1;
     static constexpr int NVP = U + 1;
-    using WS = IpmWs<NVS, MR>;
-    using WP = IpmWs<NVP, MR>;
-    static constexpr int MRP = 32 * MR;
+    using WS = IpmWs<NVS, MRC>;
+    using WP = IpmWs<NVP, MRC>;
+    static constexpr int MRP = 32 * MRC;
     static constexpr int Y = U + NX + 1;
-    static constexpr int kDoubles = WS::kDoubles;
-    // scratch inside the simplex block's s/lam/a/b region (4*MRP doubles)
-    static constexpr int oM = WS::oS;               // candidate M, later Mp (Y*Y)
+    // assembly scratch behind the solver block (cost transform, simplex geometry)
+    static constexpr int oM = WS::kDoubles;         // candidate M, later Mp (Y*Y)
     static constexpr int oT = oM + Y * Y;           // T (Y*Y)
     static constexpr int oMT = oT + Y * Y;          // M*T (Y*Y)
     static constexpr int oR = oMT + Y * Y;          // simplex vertices (NX+1)*NX
     static constexpr int oE = oR + (NX + 1) * NX;   // E NX*NX
     static constexpr int oV = oE + NX * NX;         // Vr (NX+1), padded 16
-    static_assert(oV + 16 <= WS::oHs, "assembly scratch must fit the row-state region");
+    static constexpr int kDoubles = oV + 16;
     static_assert(WP::kDoubles <= WS::kDoubles, "point block must fit the simplex block");
 };
 
@@ -63,11 +73,22 @@ struct SolveOut {
     double flops; // algorithmic flops spent (see ipm_solve)
 };
 
-template <int NV, int MR>
+// bit j set <=> row lane+32*j < nrows
+template <int MRC>
+__device__ __forceinline__ unsigned act_of(int nrows, int lane)
+{
+    unsigned a = 0;
+#pragma unroll
+    for (int j = 0; j < MRC; ++j)
+        if (lane + 32 * j < nrows) a |= 1u << j;
+    return a;
+}
+
+template <int NV, int MRC>
 __device__ __forceinline__ int run_ipm(double *ws, unsigned act, int lane, SolveOut &out, double &obj)
 {
-    using W = IpmWs<NV, MR>;
-    const int st = ipm_solve<NV, MR>(ws, act, lane);
+    using W = IpmWs<NV, MRC>;
+    const int st = ipm_solve<NV, MRC>(ws, act, lane);
     obj = ws[W::oOut + 0];
     out.iters += (int)ws[W::oOut + 1];
     out.flops += ws[W::oOut + 2];
@@ -76,14 +97,31 @@ __device__ __forceinline__ int run_ipm(double *ws, unsigned act, int lane, Solve
     return st;
 }
 
+// zero rows [from, 32*MRC) of an NV-column tile (G = 0, h = 1: the ipm_solve contract for rows
+// that do not take part)
+template <int NV, int MRC>
+__device__ __forceinline__ void clear_rows(double *Gs, double *hs, int from, int lane)
+{
+    constexpr int MRP = 32 * MRC;
+#pragma unroll
+    for (int j = 0; j < MRC; ++j) {
+        const int r = lane + 32 * j;
+        if (r >= from) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) Gs[k * MRP + r] = 0.0;
+            hs[r] = 1.0;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
-// P_theta_delta at one theta for candidate c.   u0 (nu values) written to u0_out by lane 0.
+// P_theta_delta at one theta for candidate c.   u0 (nu values) written to u0_out.
 // ---------------------------------------------------------------------------------------
-template <int U, int NX, int MR>
+template <int U, int NX, int MRI, int MRC>
 __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__restrict__ theta,
                                 double *ws, double *u0_out, int lane)
 {
-    using W = typename WarpWs<U, NX, MR>::WP;
+    using W = typename WarpWs<U, NX, MRI, MRC>::WP;
     constexpr int MRP = W::MRP, NV = U + 1;
     double *Gs = ws + W::oG, *hs = ws + W::oH, *Hs = ws + W::oHs, *fs = ws + W::oF, *zs = ws + W::oZ;
     SolveOut out{0, 0.0, 0, 0, 0.0};
@@ -93,20 +131,26 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
     double th[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) th[i] = theta[i];
-    unsigned act = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
     bool viol = false;
     double s0 = 0.0;
 #pragma unroll 1
-    for (int j = 0; j < MR; ++j) {
+    for (int j = 0; j < MRI; ++j) {
         const int r = lane + 32 * j;
+        bool keep = false;
+        double g[U], hv = 0.0;
+#pragma unroll
+        for (int k = 0; k < U; ++k) g[k] = 0.0;
         if (r < m) {
-            double g[U], nrm = 0.0;
+            double nrm = 0.0, l1 = 0.0;
 #pragma unroll
             for (int k = 0; k < U; ++k) {
                 g[k] = Gc[k * MP + r];
                 nrm = fmax(nrm, fabs(g[k]));
+                l1 += fabs(g[k]);
             }
-            double hv = gc[r];
+            hv = gc[r];
 #pragma unroll
             for (int i = 0; i < NX; ++i) hv = fma(Sc[i * MP + r], th[i], hv);
             const double rho = rc[r];
@@ -115,21 +159,32 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
                 if (hv < -EHM_TAU_CONST * sc) viol = true;
             } else {
                 const double inv = 1.0 / nrm;
+                hv *= inv;
 #pragma unroll
-                for (int k = 0; k < U; ++k) Gs[k * MRP + r] = g[k] * inv;
-                Gs[U * MRP + r] = -1.0;
-                hs[r] = hv * inv;
-                s0 = fmax(s0, -hv * inv);
-                act |= 1u << j;
+                for (int k = 0; k < U; ++k) g[k] *= inv;
+                keep = !(l1 * inv <= hv - EHM_TAU_DROP);   // pre-solve: cannot bind in |u| <= 1
             }
         }
-        if (!(act >> j & 1u)) {  // rows that do not take part: G = 0, h = 1 (ipm_solve contract)
+        const unsigned bal = __ballot_sync(kFull, keep);
+        if (keep) {
+            const int pos = cnt + __popc(bal & lt);
+            if (pos < MRP) {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) Gs[k * MRP + r] = 0.0;
-            hs[r] = 1.0;
+                for (int k = 0; k < U; ++k) Gs[k * MRP + pos] = g[k];
+                Gs[U * MRP + pos] = -1.0;
+                hs[pos] = hv;
+            }
+            s0 = fmax(s0, -hv);
         }
+        cnt += __popc(bal);
     }
     if (__any_sync(kFull, viol)) return out;
+    if (cnt > MRP) {  // capacity of the compacted tile exceeded (never for the shipped examples)
+        out.status = -1;
+        return out;
+    }
+    clear_rows<NV, MRC>(Gs, hs, cnt, lane);
+    const unsigned act = act_of<MRC>(cnt, lane);
     s0 = warp_max(s0);
     // ---- phase 1: min sigma s.t. G u - sigma <= h --------------------------------------
     for (int e = lane; e < NV * NV; e += 32) Hs[e] = 0.0;
@@ -139,7 +194,7 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
     }
     __syncwarp();
     double obj;
-    int st = run_ipm<NV, MR>(ws, act, lane, out, obj);
+    int st = run_ipm<NV, MRC>(ws, act, lane, out, obj);
     if (st != 0) {
         out.status = -1;
         return out;
@@ -166,9 +221,8 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
             const int a = e / NV, b = e % NV;
             Hs[e] = (a < U && b < U) ? 2.0 * Mc[a * Y + b] / cs : 0.0;
         }
-#pragma unroll 1
-        for (int j = 0; j < MR; ++j)
-            if (act >> j & 1u) Gs[U * MRP + lane + 32 * j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < MRC; ++j) Gs[U * MRP + lane + 32 * j] = 0.0;
         cst = Mc[(Y - 1) * Y + Y - 1];
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
@@ -178,7 +232,7 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
         }
         __syncwarp();
     }
-    st = run_ipm<NV, MR>(ws, act, lane, out, obj);
+    st = run_ipm<NV, MRC>(ws, act, lane, out, obj);
     if (st != 0) {
         out.status = -1;
         return out;
@@ -194,13 +248,15 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
 // Simplex problems.  Rv: (NX+1)*NX vertices (global), Vr: NX+1 vertex costs (global, TQP).
 // mode: EHM_SX_ALIVE / EHM_SX_TQP / EHM_SX_MINV;  phase1: run the alive test first.
 // sol (optional, global, NX+1 doubles): [beta*, V*] written for TQP / MINV.
+// Row order of the compacted tile: surviving stage rows, the NX+1 simplex rows, then (TQP)
+// the two epigraph rows -- so phase 1 simply runs on the first total-2 rows.
 // ---------------------------------------------------------------------------------------
-template <int U, int NX, int MR>
+template <int U, int NX, int MRI, int MRC>
 __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__restrict__ Rv,
                                   const double *__restrict__ Vr, int mode, bool phase1,
                                   double *ws, double *sol, int lane)
 {
-    using WW = WarpWs<U, NX, MR>;
+    using WW = WarpWs<U, NX, MRI, MRC>;
     using W = typename WW::WS;
     constexpr int MRP = W::MRP, NB = U + NX, NVS = U + NX + 1, Y = WW::Y;
     double *Gs = ws + W::oG, *hs = ws + W::oH, *Hs = ws + W::oHs, *fs = ws + W::oF, *zs = ws + W::oZ,
@@ -225,19 +281,26 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         for (int i = 0; i <= NX; ++i) cs = fmax(cs, fabs(Vs[i]));
     }
     const bool tau = (mode == EHM_SX_TQP);
-    unsigned act = 0, tau_bits = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
     bool viol = false;
     double s0 = 0.0;
+    // ---- stage rows: normalise, pre-solve, compact ------------------------------------------
 #pragma unroll 1
-    for (int j = 0; j < MR; ++j) {
+    for (int j = 0; j < MRI; ++j) {
         const int r = lane + 32 * j;
-        double co[NB], hv = 0.0, rho = 1.0, last = 0.0;
-        bool have = false;
+        bool keep = false;
+        double co[NB], hv = 0.0;
 #pragma unroll
         for (int k = 0; k < NB; ++k) co[k] = 0.0;
         if (r < m) {
+            double nrm = 0.0, l1 = 0.0, bmax = 0.0;
 #pragma unroll
-            for (int k = 0; k < U; ++k) co[k] = Gc[k * MP + r];
+            for (int k = 0; k < U; ++k) {
+                co[k] = Gc[k * MP + r];
+                nrm = fmax(nrm, fabs(co[k]));
+                l1 += fabs(co[k]);
+            }
             double sr[NX];
             hv = gc[r];
 #pragma unroll
@@ -251,22 +314,57 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
 #pragma unroll
                 for (int jj = 0; jj < NX; ++jj) v = fma(sr[jj], Es[jj * NX + i], v);
                 co[U + i] = -v;
+                nrm = fmax(nrm, fabs(v));
+                bmax = fmax(bmax, -v);
             }
-            rho = rc[r];
-            have = true;
-        } else if (r < m + NX) {  // -beta_i <= 0
-            const int i = r - m;
+            const double rho = rc[r];
+            const double sc = rho > 0.0 ? rho : 1.0;
+            if (nrm <= EHM_ZERO_ROW * sc) {
+                if (hv < -EHM_TAU_CONST * sc) viol = true;
+            } else {
+                const double inv = 1.0 / nrm;
+                hv *= inv;
 #pragma unroll
-            for (int k = 0; k < NX; ++k) co[U + k] = (k == i) ? -1.0 : 0.0;
-            have = true;
-        } else if (r == m + NX) {  // sum beta <= 1
+                for (int k = 0; k < NB; ++k) co[k] *= inv;
+                // sup over |u| <= 1 and beta in the simplex of the row's left-hand side
+                keep = !((l1 + bmax) * inv <= hv - EHM_TAU_DROP);
+            }
+        }
+        const unsigned bal = __ballot_sync(kFull, keep);
+        if (keep) {
+            const int pos = cnt + __popc(bal & lt);
+            if (pos < MRP) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k) Gs[k * MRP + pos] = co[k];
+                Gs[NB * MRP + pos] = 0.0;
+                hs[pos] = hv;
+            }
+            s0 = fmax(s0, -hv);
+        }
+        cnt += __popc(bal);
+    }
+    if (__any_sync(kFull, viol)) return out;
+    // ---- simplex rows (-beta_i <= 0, sum beta <= 1) and the two epigraph rows ---------------
+    const int nextra = NX + 1 + (tau ? 2 : 0);
+    if (cnt + nextra > MRP) {
+        out.status = -1;
+        return out;
+    }
+    if (lane < nextra) {
+        const int pos = cnt + lane;
+        double co[NB], last = 0.0, hv = 0.0;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) co[k] = 0.0;
+        if (lane < NX) {
+#pragma unroll
+            for (int k = 0; k < NX; ++k) co[U + k] = (k == lane) ? -1.0 : 0.0;
+        } else if (lane == NX) {
 #pragma unroll
             for (int k = 0; k < NX; ++k) co[U + k] = 1.0;
             hv = 1.0;
-            have = true;
-        } else if (tau && r <= m + NX + 2) {
+        } else {
             // bar_V(beta) = Vr0 + dc'beta;  tau' scaled by cs   (oracle.py:88-95)
-            const double k2 = (r == m + NX + 1) ? 1.0 : 1.0 / (1.0 + tb.eps_r);
+            const double k2 = (lane == NX + 1) ? 1.0 : 1.0 / (1.0 + tb.eps_r);
             double n1 = cs;
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
@@ -274,48 +372,29 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
                 co[U + i] = -dc;
                 n1 = fmax(n1, fabs(dc));
             }
-            last = -cs;
-            hv = (r == m + NX + 1) ? Vs[0] - tb.eps_a : Vs[0] * k2;
-            rho = n1;
-            have = true;
-            tau_bits |= 1u << j;
-        }
-        if (have) {
-            double nrm = fabs(last);
+            const double inv = 1.0 / n1;
 #pragma unroll
-            for (int k = 0; k < NB; ++k) nrm = fmax(nrm, fabs(co[k]));
-            const double sc = rho > 0.0 ? rho : 1.0;
-            if (nrm <= EHM_ZERO_ROW * sc) {
-                if (hv < -EHM_TAU_CONST * sc) viol = true;
-            } else {
-                const double inv = 1.0 / nrm;
-#pragma unroll
-                for (int k = 0; k < NB; ++k) Gs[k * MRP + r] = co[k] * inv;
-                Gs[NB * MRP + r] = last * inv;  // tau column
-                hs[r] = hv * inv;
-                // rows carrying tau do not exist in the phase-1 problem
-                if (!(tau_bits >> j & 1u)) s0 = fmax(s0, -hv * inv);
-                act |= 1u << j;
-            }
+            for (int i = 0; i < NX; ++i) co[U + i] *= inv;
+            last = -cs * inv;
+            hv = ((lane == NX + 1) ? Vs[0] - tb.eps_a : Vs[0] * k2) * inv;
         }
-        if (!(act >> j & 1u)) {  // rows that do not take part: G = 0, h = 1 (ipm_solve contract)
 #pragma unroll
-            for (int k = 0; k < NVS; ++k) Gs[k * MRP + r] = 0.0;
-            hs[r] = 1.0;
-        }
+        for (int k = 0; k < NB; ++k) Gs[k * MRP + pos] = co[k];
+        Gs[NB * MRP + pos] = last;
+        hs[pos] = hv;
+        if (lane <= NX) s0 = fmax(s0, -hv);
     }
-    if (__any_sync(kFull, viol)) return out;
+    const int total = cnt + nextra, n1rows = cnt + NX + 1;
+    clear_rows<NVS, MRC>(Gs, hs, total, lane);
     s0 = warp_max(s0);
     __syncwarp();
     double obj;
     if (phase1 || mode == EHM_SX_ALIVE) {
-        // sigma column: -1 on every phase-1 row; the tau column is restored afterwards from
-        // registers (two rows at most)
-        const unsigned act1 = act & ~tau_bits;
-        double keep0 = 0.0;  // tau-column value of this lane's non-tau rows is 0
-        (void)keep0;
-#pragma unroll 1
-        for (int j = 0; j < MR; ++j)
+        // sigma column: -1 on the phase-1 rows, restored to 0 afterwards (the epigraph rows keep
+        // their tau coefficient: they sit behind n1rows and are masked out of this solve)
+        const unsigned act1 = act_of<MRC>(n1rows, lane);
+#pragma unroll
+        for (int j = 0; j < MRC; ++j)
             if (act1 >> j & 1u) Gs[NB * MRP + lane + 32 * j] = -1.0;
         for (int e = lane; e < NVS * NVS; e += 32) Hs[e] = 0.0;
         if (lane < 16) {
@@ -323,7 +402,7 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
             zs[lane] = (lane == NB) ? s0 + 1.0 : 0.0;
         }
         __syncwarp();
-        const int st = run_ipm<NVS, MR>(ws, act1, lane, out, obj);
+        const int st = run_ipm<NVS, MRC>(ws, act1, lane, out, obj);
         if (st != 0) {
             out.status = -1;
             return out;
@@ -334,16 +413,9 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
             return out;
         }
         if (!(obj <= -EHM_TAU_INT)) return out;
-#pragma unroll 1
-        for (int j = 0; j < MR; ++j)
+#pragma unroll
+        for (int j = 0; j < MRC; ++j)
             if (act1 >> j & 1u) Gs[NB * MRP + lane + 32 * j] = 0.0;
-        // the row-state region was clobbered by the solver: reload the geometry scratch
-        for (int e = lane; e < (NX + 1) * NX; e += 32) Rs[e] = Rv[e];
-        __syncwarp();
-        for (int e = lane; e < NX * NX; e += 32) {
-            const int j = e / NX, i = e % NX;
-            Es[e] = Rs[(i + 1) * NX + j] - Rs[j];
-        }
         __syncwarp();
     }
     // ---- cost in [u; beta; 1]: Mp = T' M T,  [u;theta;1] = T [u;beta;1] ----------------
@@ -392,7 +464,8 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         zs[lane] = 0.0;
     }
     __syncwarp();
-    const int st = run_ipm<NVS, MR>(ws, act, lane, out, obj);
+    const unsigned act = act_of<MRC>(total, lane);
+    const int st = run_ipm<NVS, MRC>(ws, act, lane, out, obj);
     if (st != 0) {
         out.status = -1;
         return out;

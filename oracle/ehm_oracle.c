@@ -250,8 +250,16 @@ static int qp_solve(int nv, int m, const double *H, const double *f, const doubl
 /* constant-row test scale-free).  returns number of kept rows, or -1 if a constant row   */
 /* is violated (problem infeasible).                                                      */
 /* ------------------------------------------------------------------------------------ */
+static int g_presolve = 1;
+void ehmo_set_presolve(int on) { g_presolve = on; }
+
+/* nbox leading variables live in [-1,1] (the scaled inputs: the input-bound rows of the MPC are
+ * part of every problem), the next nsx are barycentric coordinates of a simplex.  Pre-solve:
+ * a normalised row a'z <= h whose left-hand side cannot exceed h - TAU_DROP anywhere in that
+ * box is dropped -- exact for every decision (see DESIGN.md "Row pre-solve"); it removes the
+ * ~75% of the reference's big-M rows (lib/mpc_library.py:529-534) that can never bind. */
 static int prep_rows(int nv, int m, const double *G, const double *h, const double *rho,
-                     double *Go, double *ho)
+                     double *Go, double *ho, int nbox, int nsx)
 {
     int mo = 0;
     for (int r = 0; r < m; ++r) {
@@ -263,6 +271,17 @@ static int prep_rows(int nv, int m, const double *G, const double *h, const doub
             continue;
         }
         double inv = 1.0 / nrm;
+        if (g_presolve) {
+            double sup = 0, bmax = 0;
+            int other = 0;
+            for (int j = 0; j < nv; ++j) {
+                double a = G[r * nv + j] * inv;
+                if (j < nbox) sup += fabs(a);
+                else if (j < nbox + nsx) bmax = fmax2(bmax, a);
+                else if (a != 0.0) other = 1;
+            }
+            if (!other && sup + bmax <= h[r] * inv - EHMO_TAU_DROP) continue;
+        }
         for (int j = 0; j < nv; ++j) Go[mo * nv + j] = G[r * nv + j] * inv;
         ho[mo] = h[r] * inv;
         ++mo;
@@ -437,7 +456,7 @@ int ehmo_p_theta_delta(ehmo_problem *pb, const double *theta, int c, double *J, 
         for (int j = 0; j < n; ++j) v += S[r * n + j] * theta[j];
         h[r] = v;
     }
-    int mo = prep_rows(U, m, G, h, rho, Gn, hn);
+    int mo = prep_rows(U, m, G, h, rho, Gn, hn, U, 0);
     if (mo >= 0) {
         int alive = phase1(pb, U, mo, Gn, hn, NULL);
         if (alive < 0) ret = -1;
@@ -628,7 +647,7 @@ static int alive_on_simplex(ehmo_problem *pb, int c, const double *R)
     simplex_qp q;
     build_simplex_qp(pb, c, R, NULL, 0, &q);
     double *Gn = dalloc((size_t)q.m * q.nv), *hn = dalloc(q.m);
-    int mo = prep_rows(q.nv, q.m, q.G, q.h, q.rho, Gn, hn);
+    int mo = prep_rows(q.nv, q.m, q.G, q.h, q.rho, Gn, hn, pb->U, pb->n);
     int ret = (mo < 0) ? 0 : phase1(pb, q.nv, mo, Gn, hn, NULL);
     free(Gn); free(hn); free_simplex_qp(&q);
     return ret;
@@ -644,7 +663,7 @@ static int solve_simplex_qp(ehmo_problem *pb, int c, const double *R, const doub
     build_simplex_qp(pb, c, R, Vr, with_tau, &q);
     double *Gn = dalloc((size_t)q.m * q.nv), *hn = dalloc(q.m);
     double z[MAXNV], obj = 0;
-    int mo = prep_rows(q.nv, q.m, q.G, q.h, q.rho, Gn, hn), st = 2;
+    int mo = prep_rows(q.nv, q.m, q.G, q.h, q.rho, Gn, hn, pb->U, pb->n), st = 2;
     if (mo >= 0) {
         st = qp_solve(q.nv, mo, q.H, q.f, Gn, hn, NULL, z, &obj, NULL);
         __sync_fetch_and_add(&pb->nsolves, 1);

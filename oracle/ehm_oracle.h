@@ -40,6 +40,7 @@ typedef struct ehmo_problem ehmo_problem;
                                  at most this much (closed feasibility, slab boundaries)      */
 #define EHMO_ZERO_ROW  1e-13  /* |coef| below this (relative to the row's natural scale)
                                  makes the row a constant row                                 */
+#define EHMO_TAU_DROP  1e-3   /* row pre-solve margin (normalised rows)                     */
 #define EHMO_MAX_ITER  80
 
 /* Switched-affine MPC description; array shapes as in
@@ -52,6 +53,7 @@ ehmo_problem *ehmo_create(int n, int nu, int N, int K, int p,
                           double eps_a, double eps_r);
 void ehmo_destroy(ehmo_problem *pb);
 void ehmo_set_eps(ehmo_problem *pb, double eps_a, double eps_r);
+void ehmo_set_presolve(int on); /* 1 (default): drop rows that cannot bind in the input box */
 int ehmo_num_candidates(const ehmo_problem *pb);
 long ehmo_solve_count(const ehmo_problem *pb); /* convex sub-problems solved so far */
 

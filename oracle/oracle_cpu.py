@@ -54,6 +54,7 @@ def lib():
         L.ehmo_bar_e.argtypes = [C.c_void_p, dp, dp, dp]
         L.ehmo_bar_d.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, dp, dp, ip]
         L.ehmo_min_over_simplex.argtypes = [C.c_void_p, dp, C.c_int, dp]
+        L.ehmo_set_presolve.argtypes = [C.c_int]
         L.ehmo_split.argtypes = [C.c_int, dp, dp, dp, ip]
         L.ehmo_simplex_volume.argtypes = [C.c_int, dp]
         L.ehmo_simplex_volume.restype = C.c_double

@@ -83,3 +83,19 @@ def test_split_matches_reference_rule(cpu_oracle):
         assert d2[k] == max(d2)
         mid = (R[ij[0]] + R[ij[1]]) / 2
         assert np.array_equal(S1[ij[0]], mid) and np.array_equal(S2[ij[1]], mid)
+
+
+def test_row_presolve_is_exact(pendulum, pendulum_roots, cpu_oracle):
+    """Dropping rows that cannot bind inside the input box |uhat| <= 1 (DESIGN.md "Row
+    pre-solve") must not change any decision: identical tree with and without it."""
+    from oracle.oracle_cpu import lib
+    from test_gpu_tree_parity import compare_trees
+    roots = pendulum_roots[[22]]
+    try:
+        lib().ehmo_set_presolve(0)
+        full = cpu_oracle.partition(roots, nthreads=4)
+    finally:
+        lib().ehmo_set_presolve(1)
+    pre = cpu_oracle.partition(roots, nthreads=4)
+    assert full['nfail'] == 0 and pre['nfail'] == 0
+    assert compare_trees(pre, full, 1) <= 1e-6
