@@ -23,7 +23,8 @@ EXPORTS = [
     'ehm_split_batch', 'ehm_partition_run', 'ehm_partition_fetch', 'ehm_partition_free',
     'ehm_read_counters', 'ehm_fp64_peak', 'ehm_hbm_peak', 'ehm_partition_create',
     'ehm_partition_advance', 'ehm_partition_export', 'ehm_partition_import',
-    'ehm_partition_fetch_origin', 'ehm_partition_set_root_ids',
+    'ehm_partition_fetch_origin', 'ehm_partition_set_root_ids', 'ehm_last_failure',
+    'ehm_debug_trace', 'ehm_debug_fetch',
 ]
 
 

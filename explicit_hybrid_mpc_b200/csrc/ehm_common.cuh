@@ -34,6 +34,7 @@ struct DevCounters {
     unsigned long long solves;  // IPM solves
     unsigned long long fails;   // numerical failures
     double flops[8];            // algorithmic flops per pipeline stage (0 = batch API)
+    int last_fail[4];           // {stage, candidate, node, iterations} of the most recent failure
 };
 
 }  // namespace ehm

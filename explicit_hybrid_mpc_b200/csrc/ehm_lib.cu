@@ -42,9 +42,14 @@ __device__ __forceinline__ long long next_item(DevCounters *cnt, int lane)
     return (long long)__shfl_sync(kFull, v, 0);
 }
 
-__device__ __forceinline__ void account(DevCounters *cnt, const SolveOut &o, int lane, int stage = 0)
+__device__ __forceinline__ void account(DevCounters *cnt, const SolveOut &o, int lane, int stage = 0,
+                                        int cand = -1, int node = -1)
 {
     if (lane == 0) {
+        if (o.status < 0) {
+            cnt->last_fail[0] = stage; cnt->last_fail[1] = cand; cnt->last_fail[2] = node;
+            cnt->last_fail[3] = o.iters;
+        }
         atomicAdd(&cnt->flops[stage], o.flops);
         atomicAdd(&cnt->iters, (unsigned long long)o.iters);
         atomicAdd(&cnt->solves, (unsigned long long)o.nsolves);
@@ -385,6 +390,15 @@ extern "C" int ehm_split_batch(int n, int B, const double *d_R, double *d_S1, do
 }
 
 // counters (host view) -- used by the Python layer and bench.py
+extern "C" int ehm_last_failure(ehm_problem *p, int32_t *info4)
+{
+    if (!p || !info4) return fail(EHM_EINVAL, "bad argument");
+    DevCounters h;
+    EHM_CUDA(cudaMemcpy(&h, p->dcnt, sizeof h, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; ++k) info4[k] = h.last_fail[k];
+    return EHM_OK;
+}
+
 extern "C" int ehm_read_counters(ehm_problem *p, int64_t *iters, int64_t *solves, int64_t *fails)
 {
     if (!p) return fail(EHM_EINVAL, "null problem");

@@ -166,7 +166,7 @@ k_lcss_ref(DevTables tb, NodeStore ns, WaveBuf wv, int W, Ctl *ctl, DevCounters 
         const SolveOut o = solve_simplex<U, NX, MRI, MRC>(tb, ns.cand[nd], ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, false,
                                                     ws, nullptr, lane);
-        account(cnt, o, lane, 1);
+        account(cnt, o, lane, 1, ns.cand[nd], nd);
         if (lane == 0) wv.tref[e] = (o.status == 1) ? o.val : INFINITY;
         __syncwarp();
     }
@@ -226,7 +226,7 @@ k_lcss_eval(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
         const SolveOut o = solve_simplex<U, NX, MRI, MRC>(tb, ec.y, ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, true, ws,
                                                     wv.it_sol + (size_t)it * (NX + 1), lane);
-        account(cnt, o, lane, 2);
+        account(cnt, o, lane, 2, ec.y, nd);
         if (lane == 0) {
             const size_t ix = (size_t)ec.x * tb.ncand + ec.y;
             if (o.status == 1) {
@@ -361,7 +361,7 @@ k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt
                 wv.ptS[slot] = o.status;
             }
         }
-        account(cnt, o, lane, 3);
+        account(cnt, o, lane, 3, pi.c, nd);
         __syncwarp();
     }
 }

@@ -153,6 +153,12 @@ int ehm_partition_free(ehm_partition *t);
 /* ---- measurement helpers (bench.py) --------------------------------------------------- */
 /* counters since problem creation */
 int ehm_read_counters(ehm_problem *p, int64_t *iters, int64_t *solves, int64_t *fails);
+/* {pipeline stage, candidate, node id, iterations} of the most recent numerical failure */
+int ehm_last_failure(ehm_problem *p, int32_t *info4);
+/* debugging aid: record the per-iteration trace {it, rp, gap, obj, rho*rd0, |lam|, rows, nv} of
+ * the solves that run while enabled (last one wins); fetch copies 128 x 8 doubles */
+int ehm_debug_trace(int on);
+int ehm_debug_fetch(double *out);
 /* dependent-free DFMA loop on every SM: the fp64 FMA roofline denominator, in TFLOP/s */
 int ehm_fp64_peak(double *tflops);
 /* STREAM-style device copy of `bytes` bytes: GB/s (read+write counted) */
