@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libehm_b200.so')
+LIB_PATH = os.environ.get('EHM_LIB_PATH') or os.path.join(_HERE, 'libehm_b200.so')   # override: kernel experiments
 
 EHM_OK, EHM_EINVAL, EHM_ECUDA, EHM_ENOMEM, EHM_EINFEASIBLE, EHM_ECAPACITY, EHM_ENUMERIC = (
     0, -1, -2, -3, -4, -5, -6)

@@ -134,48 +134,46 @@ struct IpmWs {
     static constexpr int oOut = oRed + 64;       // [0] objective [1] iterations [2] flops (8)
     static constexpr int oLs = oOut + 8;         // packed Cholesky factor / working matrix (64)
     static constexpr int oD0 = oLs + 64;         // original diagonal of K (16)
-    static constexpr int oScr = oD0 + 16;        // 8 x 33 transposition scratch of the reductions
-    static constexpr int kDoubles = oScr + 8 * 33;
+    static constexpr int oScr = oD0 + 16;        // 32 x 33 transposition scratch of the reductions
+    static constexpr int kDoubles = oScr + 32 * 33;
 };
 
-// Warp sum of 8 per-lane values through shared memory: the 8x32 partials are transposed through
-// a padded 8x33 scratch (2-way bank conflicts only, the minimum for 64-bit words), lane L adds 8
-// of the 32 partials of value L/4, two shuffle stages finish.  Returns the sum of value L/4.
-// Shared memory instead of a shuffle tree because every 64-bit shuffle costs ~12 SASS
-// instructions here; the unrolled reduce-scatter of the 55 normal-matrix entries alone was
-// 2.7k instructions and pushed the solver loop out of the instruction cache (profiles/).
-__device__ __noinline__ double chunk_reduce8(double v0, double v1, double v2, double v3, double v4,
-                                              double v5, double v6, double v7, double *scr, int lane)
-{
-    scr[0 * 33 + lane] = v0;
-    scr[1 * 33 + lane] = v1;
-    scr[2 * 33 + lane] = v2;
-    scr[3 * 33 + lane] = v3;
-    scr[4 * 33 + lane] = v4;
-    scr[5 * 33 + lane] = v5;
-    scr[6 * 33 + lane] = v6;
-    scr[7 * 33 + lane] = v7;
-    __syncwarp();
-    const double *q = scr + (lane >> 2) * 33 + (lane & 3) * 8;
-    double a = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
-    a += __shfl_xor_sync(kFull, a, 1);
-    a += __shfl_xor_sync(kFull, a, 2);
-    __syncwarp();
-    return a;
-}
+// Warp sums through shared memory.  Up to 32 per-lane values at a time are transposed through
+// a 32x33 scratch: every lane stores its partial of value i at scr[i*33 + lane] (unit stride:
+// conflict free), then lane L adds the 32 partials of value L (addresses L*33 + j: 16 distinct
+// 8-byte banks per half-warp: conflict free) in a depth-5 tree.  No shuffles: a 64-bit shuffle
+// costs ~12 SASS instructions here and the earlier 8-value version of this routine (11 dependent
+// calls per iteration) was 22 % of all stall samples (profiles/README.md).
+constexpr int kScrStride = 33;
 
-// Sum CNT (<= 8*NCH) per-lane partials v[] over the warp into out[0..CNT) (shared memory).
-template <int NCH, int P>
-__device__ __forceinline__ void reduce_chunks(const double (&v)[P], double *out, int cnt, double *scr, int lane)
+// Sum CNT per-lane partials v[base .. base+CNT) over the warp into out[base .. base+CNT).
+template <int CNT, int P>
+__device__ __forceinline__ void reduce_round(const double (&v)[P], int base, double *out, double *scr, int lane)
 {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const double r = chunk_reduce8(v[8 * c + 0], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3], v[8 * c + 4],
-                                       v[8 * c + 5], v[8 * c + 6], v[8 * c + 7], scr, lane);
-        const int idx = 8 * c + (lane >> 2);
-        if ((lane & 3) == 0 && idx < cnt) out[idx] = r;
+    for (int i = 0; i < CNT; ++i) scr[i * kScrStride + lane] = v[base + i];
+    __syncwarp();
+    if (lane < CNT) {
+        const double *q = scr + lane * kScrStride;
+        double t[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = q[j] + q[j + 16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] += t[j + 8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] += t[j + 4];
+        out[base + lane] = (t[0] + t[2]) + (t[1] + t[3]);
     }
     __syncwarp();
+}
+
+// Sum the first CNT of P per-lane partials over the warp into out[0..CNT) (shared memory).
+template <int CNT, int P>
+__device__ __forceinline__ void reduce_all(const double (&v)[P], double *out, double *scr, int lane)
+{
+    constexpr int R0 = CNT < 32 ? CNT : 32;
+    reduce_round<R0>(v, 0, out, scr, lane);
+    if constexpr (CNT > 32) reduce_round<CNT - 32>(v, 32, out, scr, lane);
 }
 
 // min over the warp of the fractions num/den (den > 0), compared by cross-multiplication so
@@ -224,6 +222,11 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         fmx = fmax(fmx, fabs(f[k]));
     }
     const double mact = warp_sum((double)__popc(act));
+    // row pairs in which no lane has a participating row are skipped (warp-uniform)
+    unsigned pairs = 0;
+#pragma unroll
+    for (int j = 0; j < MR; j += 2)
+        if (__any_sync(kFull, (act >> j & 3u) != 0u)) pairs |= 1u << j;
     // ---- centred start + initial dual residual rd0 = |H z0 + f + G' lam0| -----------------
     double rd0;
     {
@@ -255,7 +258,7 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
 #pragma unroll
             for (int k = 0; k < NV; ++k) gl[k] = fma(g[k], l, gl[k]);
         }
-        reduce_chunks<PV / 8>(gl, red, NV, scr, lane);
+        reduce_all<NV>(gl, red, scr, lane);
         double m = 0.0;
         if (lane < NV) {
             double hz = w[W::oF + lane] + red[lane];
@@ -278,6 +281,7 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         double mu = 0.0, rpm = 0.0, lmx = 0.0;
 #pragma unroll 1
         for (int j = 0; j < MR; j += 2) {
+            if (!(pairs >> j & 1u)) continue;
             const bool on1 = (j + 1 < MR);
             const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
             // rows that do not take part in THIS solve (e.g. the epigraph rows during phase 1)
@@ -347,35 +351,45 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         }
         if (it == EHM_MAX_ITER) break;
         const double mu_mean = mu / mact;
-        // ---- K -> packed scratch -> lane-parallel Cholesky (rows in registers, pivot rows
-        //      broadcast by shuffle) -> packed factor in shared memory (read by broadcast) -----
-        reduce_chunks<PK / 8>(acc, red, NK, scr, lane);
+        // ---- K -> packed scratch -> Cholesky, redundantly in every lane's registers (SIMT makes
+        //      the redundancy free; the lane-parallel shuffle version cost 1.5k instructions:
+        //      a 64-bit shuffle is ~13 SASS instructions) -> packed factor in shared memory -----
+        reduce_all<NK>(acc, red, scr, lane);
         double inv[NV];
         {
-            double Lr[NV], d0 = 1.0;
-            const int li = lane < NV ? lane : 0;
+            double Lk[NK];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) Lr[k] = (k <= li) ? red[tri(li, k)] + Hs[li * NV + k] : 0.0;
-            d0 = red[tri(li, li)] + Hs[li * NV + li];
+            for (int i = 0; i < NV; ++i)
+#pragma unroll
+                for (int q = 0; q <= i; ++q) Lk[tri(i, q)] = red[tri(i, q)] + Hs[i * NV + q];
             __syncwarp();
             bool bad = false;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-                double v = Lr[j];
+                const double d0 = Lk[tri(j, j)];
+                double d = d0;
 #pragma unroll
-                for (int k = 0; k < j; ++k) v = fma(-Lr[k], __shfl_sync(kFull, Lr[k], j), v);
-                double d = __shfl_sync(kFull, v, j);
-                const double dd0 = __shfl_sync(kFull, d0, j);
+                for (int k = 0; k < j; ++k) d = fma(-Lk[tri(j, k)], Lk[tri(j, k)], d);
                 if (!isfinite(d)) bad = true;
-                if (d <= 1e-13 * dd0 || dd0 <= 0.0) d = 1e100;   // pivot guard (oracle: cholesky)
+                if (d <= 1e-13 * d0 || d0 <= 0.0) d = 1e100;   // pivot guard (oracle: cholesky)
                 const double iv = rsqrt(d);
                 inv[j] = iv;
-                Lr[j] = (lane == j) ? d * iv : v * iv;
-                if (lane >= j && lane < NV) Ls[tri(li, j)] = Lr[j];
+                Lk[tri(j, j)] = d * iv;
+#pragma unroll
+                for (int i = j + 1; i < NV; ++i) {
+                    double v = Lk[tri(i, j)];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) v = fma(-Lk[tri(i, k)], Lk[tri(j, k)], v);
+                    Lk[tri(i, j)] = v * iv;
+                }
             }
             if (bad) {
                 status = 2;
                 break;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < NK; ++k) Ls[k] = Lk[k];
             }
             __syncwarp();
         }
@@ -389,6 +403,7 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
             for (int k = 0; k < PV; ++k) rh[k] = 0.0;
 #pragma unroll 1
             for (int j = 0; j < MR; j += 2) {
+                if (!(pairs >> j & 1u)) continue;
                 const bool on1 = (j + 1 < MR);
                 const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
                 const double m0 = (act >> j & 1u) ? 1.0 : 0.0;
@@ -416,7 +431,7 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
 #pragma unroll
                 for (int k = 0; k < NV; ++k) rh[k] = fma(g0[k], q0, fma(g1[k], q1, rh[k]));
             }
-            reduce_chunks<PV / 8>(rh, red, NV, scr, lane);
+            reduce_all<NV>(rh, red, scr, lane);
 #pragma unroll
             for (int k = 0; k < NV; ++k) dz[k] = -cres * hzf[k] - red[k];
             __syncwarp();
@@ -439,6 +454,7 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
             ad = 1.0;
 #pragma unroll 1
             for (int j = 0; j < MR; j += 2) {
+                if (!(pairs >> j & 1u)) continue;
                 const bool on1 = (j + 1 < MR);
                 const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
                 const double m1 = (on1 && (act >> (j + 1) & 1u)) ? 1.0 : 0.0;
@@ -488,6 +504,7 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         for (int k = 0; k < NV; ++k) z[k] = fma(alpha, dz[k], z[k]);
 #pragma unroll 1
         for (int j = 0; j < MR; ++j) {
+            if (!(act >> j & 1u)) continue;
             const int r = lane + 32 * j;
             sv[r] = fma(alpha, av[r], sv[r]);
             lv[r] = fma(alpha, bv[r], lv[r]);
