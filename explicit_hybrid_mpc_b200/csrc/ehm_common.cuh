@@ -45,6 +45,7 @@ struct ehm_problem {
     double *dG = nullptr, *dS = nullptr, *dg = nullptr, *drho = nullptr, *dM = nullptr;
     ehm::DevCounters *dcnt = nullptr;
     int sm_count = 148;
+    void *parked = nullptr;   // one retired ehm_partition whose device buffers are reused
     std::vector<double> u_dummy;
 };
 

@@ -29,6 +29,8 @@ static int find_cfg(int U, int NX, int rows_total)
     return -1;
 }
 
+static void ehm_partition_free_now(void *t);   // defined with ehm_partition below
+
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
@@ -300,6 +302,10 @@ extern "C" int ehm_problem_create(const ehm_problem_desc *desc, ehm_problem **ou
 extern "C" int ehm_problem_destroy(ehm_problem *p)
 {
     if (!p) return EHM_OK;
+    if (p->parked) {
+        ehm_partition_free_now(p->parked);
+        p->parked = nullptr;
+    }
     cudaFree(p->dG); cudaFree(p->dS); cudaFree(p->dg); cudaFree(p->drho); cudaFree(p->dM);
     cudaFree(p->dcnt);
     delete p;
@@ -448,6 +454,8 @@ struct ehm_partition {
     }
 };
 
+static void ehm_partition_free_now(void *t) { delete (ehm_partition *)t; }
+
 namespace {
 
 void fill_stats(ehm_partition *t, ehm_partition_stats *stats)
@@ -587,20 +595,33 @@ extern "C" int ehm_partition_create(ehm_problem *p, int nroots, const double *ro
     const int64_t maxn = o.max_nodes > 0 ? o.max_nodes : (int64_t)1 << 22;
     const int64_t fcap = o.max_frontier > 0 ? o.max_frontier : std::max<int64_t>(65536, 16 * (int64_t)W);
     if (maxn > 0x7ffffff0ll || fcap > 0x7ffffff0ll || nroots > maxn) return fail(EHM_EINVAL, "capacity too large");
-    ehm_partition *t = new ehm_partition();
+    // device buffers (several GB) are recycled: ehm_partition_free parks one object per problem
+    ehm_partition *t = nullptr;
+    if (p->parked) {
+        ehm_partition *c = (ehm_partition *)p->parked;
+        p->parked = nullptr;
+        if (c->ns.cap == (int)maxn && c->fr.cap == (int)fcap && c->wv.W == W) t = c;
+        else delete c;
+    }
+    const bool recycled = (t != nullptr);
+    if (!t) t = new ehm_partition();
     t->pb = p; t->n = n; t->nu = nu; t->opts = o;
+    t->ecc_q0 = 0; t->device_ms = 0; t->launches = 0; t->waves = 0;
+    for (int k = 0; k < 8; ++k) { t->sms[k] = 0; t->sbytes[k] = 0; }
     int rc = EHM_OK;
     auto A = [&](int r) { if (rc == EHM_OK) rc = r; };
     NodeStore &ns = t->ns;
+    Frontier &fr = t->fr;
+    WaveBuf &wv = t->wv;
+    EccBuf &eb = t->eb;
+    if (!recycled) {
     ns.cap = (int)maxn;
     A(t->alloc(&ns.verts, (size_t)maxn * (n + 1) * n)); A(t->alloc(&ns.vcost, (size_t)maxn * (n + 1)));
     A(t->alloc(&ns.vinput, (size_t)maxn * (n + 1) * nu)); A(t->alloc(&ns.cand, maxn));
     A(t->alloc(&ns.left, maxn)); A(t->alloc(&ns.right, maxn)); A(t->alloc(&ns.root_id, maxn));
     A(t->alloc(&ns.depth, maxn)); A(t->alloc(&ns.closed, maxn)); A(t->alloc(&ns.origin, (size_t)2 * maxn));
-    Frontier &fr = t->fr;
     fr.cap = (int)fcap;
     A(t->alloc(&fr.node, fcap)); A(t->alloc(&fr.skip, fcap)); A(t->alloc(&fr.lb, (size_t)fcap * ncand));
-    WaveBuf &wv = t->wv;
     wv.W = W;
     const size_t WN = (size_t)W * ncand;
     A(t->alloc(&wv.node, W)); A(t->alloc(&wv.skip, W)); A(t->alloc(&wv.lb, WN)); A(t->alloc(&wv.tref, W));
@@ -612,11 +633,11 @@ extern "C" int ehm_partition_create(ehm_problem *p, int nroots, const double *ro
     A(t->alloc(&wv.pitems, PP)); A(t->alloc(&wv.ptJ, (size_t)W * (kSelT + 1) * (n + 2)));
     A(t->alloc(&wv.ptU, (size_t)W * (kSelT + 1) * (n + 2) * nu)); A(t->alloc(&wv.ptS, (size_t)W * (kSelT + 1) * (n + 2)));
     A(t->alloc(&wv.minv, W)); A(t->alloc(&wv.minv_st, W));
-    EccBuf &eb = t->eb;
     A(t->alloc(&eb.queue, maxn)); A(t->alloc(&eb.J, (size_t)kEccWave * ncand * (n + 2)));
     A(t->alloc(&eb.U, (size_t)kEccWave * ncand * (n + 1) * nu)); A(t->alloc(&eb.S, (size_t)kEccWave * ncand * (n + 2)));
     A(t->alloc(&eb.pick, kEccWave));
     A(t->alloc(&t->dctl, 1));
+    }
     if (rc != EHM_OK) { delete t; return rc; }
     // root nodes
     {
@@ -810,7 +831,10 @@ extern "C" int ehm_partition_fetch(ehm_partition *t, int32_t *left, int32_t *rig
 
 extern "C" int ehm_partition_free(ehm_partition *t)
 {
-    delete t;
+    if (!t) return EHM_OK;
+    ehm_problem *p = t->pb;
+    if (p && !p->parked) p->parked = t;   // keep the device buffers for the next run
+    else delete t;
     return EHM_OK;
 }
 
