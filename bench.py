@@ -129,6 +129,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--wave', type=int, default=0, help='frontier entries per wave (0: library default)')
+    ap.add_argument('--round-ms', type=float, default=0.0,
+                    help='N>1: meet every so many ms instead of on a starvation flag (0: flag)')
+    ap.add_argument('--fill', type=int, default=256, help='N>1: frontier depth below which a rank asks for work')
+    ap.add_argument('--deal', type=int, default=512, help='N>1: frontier depth per rank at which the one-off shuffle happens')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -170,12 +175,15 @@ def main():
             dist.barrier()
         t0 = time.perf_counter()
         if world == 1:
-            res = partition(orc, roots)
+            res = partition(orc, roots, wave=args.wave)
             info = dict(exchange_s=0.0, rounds=0, records_sent=0)
         else:
             # one partition job over all ranks: sharded frontier + all-to-all rebalance; the
             # stitched tree is gathered to rank 0 inside the timed region (end-to-end)
-            res, info = partition_distributed(orc, roots, gather=True)
+            res, info = partition_distributed(orc, roots, gather=True, wave=args.wave or 1024,
+                                              waves_per_round=1 if args.round_ms <= 0 else 0,
+                                              round_ms=args.round_ms, signal=args.round_ms <= 0,
+                                              fill_depth=args.fill, deal_depth=args.deal)
             if res is None:
                 res = type('R', (), dict(stats=info['stats'], nnodes=info['stats']['nnodes']))()
             else:
@@ -285,9 +293,13 @@ def main():
                     eps_a=eps_a, leaves_per_step=leaves_all / args.steps,
                     nodes_per_step=nn if world == 1 else None,
                     parallelism=('single GPU' if world == 1 else 'frontier sharded over %d ranks: roots dealt '
-                                 'round-robin, NCCL all-gather of depths every 2 waves, all-to-all of '
-                                 'frontier records only when depths diverge (%d rounds, %d records in the '
-                                 'last step)' % (world, xch[-1]['rounds'], xch[-1]['records_sent'])),
+                                 'round-robin; ranks meet (all-gather of depths) when one raises a starvation flag%s; '
+                                 'NCCL all-to-all of frontier records: one interleaved shuffle after the ramp-up, '
+                                 'then surplus -> starving ranks (%d meetings, %d exchanges, %d records sent by '
+                                 'rank 0 in the last step)'
+                                 % (world, '' if args.round_ms <= 0 else ' / every %.0f ms' % args.round_ms,
+                                    xch[-1].get('meetings', 0), xch[-1]['rounds'], xch[-1]['records_sent'])),
+                    wave=(args.wave or 4096) if world == 1 else (args.wave or 1024),
                     l2='flushed between timed iterations (256 MiB write)'),
         e2e=dict(value=e2e, unit='leaves/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
         oracle_solves_per_s=solves_all / dev_s,

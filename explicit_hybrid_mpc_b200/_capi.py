@@ -22,7 +22,7 @@ EXPORTS = [
     'ehm_last_error', 'ehm_kernel_launches', 'ehm_qp_theta_delta_batch', 'ehm_simplex_batch',
     'ehm_split_batch', 'ehm_partition_run', 'ehm_partition_fetch', 'ehm_partition_free',
     'ehm_read_counters', 'ehm_fp64_peak', 'ehm_hbm_peak', 'ehm_partition_create',
-    'ehm_partition_advance', 'ehm_partition_export', 'ehm_partition_import',
+    'ehm_partition_advance', 'ehm_partition_advance_for', 'ehm_partition_export', 'ehm_partition_import',
     'ehm_partition_fetch_origin', 'ehm_partition_set_root_ids', 'ehm_last_failure',
     'ehm_debug_trace', 'ehm_debug_fetch',
 ]
@@ -48,7 +48,7 @@ class PartitionOpts(C.Structure):
 
 class PartitionStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ('nnodes', 'nleaves', 'nsolves', 'niters', 'nfail',
-                                         'nwaves', 'nlaunches', 'open_left')] + \
+                                         'nwaves', 'nlaunches', 'open_left', 'frontier')] + \
                [('max_depth', C.c_int), ('device_ms', C.c_double),
                 ('stage_ms', C.c_double * 8), ('stage_flops', C.c_double * 8),
                 ('stage_bytes', C.c_double * 8)]
@@ -87,6 +87,7 @@ def lib():
             L.ehm_partition_create.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
                                                C.POINTER(PartitionOpts), C.POINTER(vp)]
             L.ehm_partition_advance.argtypes = [vp, C.c_int64, C.POINTER(PartitionStats)]
+            L.ehm_partition_advance_for.argtypes = [vp, C.c_int64, C.c_double, C.POINTER(PartitionStats)]
             L.ehm_partition_export.argtypes = [vp, C.c_int, vp, vp, vp]
             L.ehm_partition_import.argtypes = [vp, C.c_int, vp, vp, vp, vp]
             L.ehm_partition_fetch_origin.argtypes = [vp, vp]

@@ -127,14 +127,16 @@ struct IpmWs {
     static constexpr int oL = oS + MRP;          // multiplier
     static constexpr int oA = oL + MRP;          // rp / ds
     static constexpr int oB = oA + MRP;          // ds.dl / rc / dl
-    static constexpr int oHs = oB + MRP;         // Hessian NV*NV row-major (zeros for an LP)
+    static constexpr int oR = oB + MRP;          // primal residual G z + s - h of the iteration
+    static constexpr int oHs = oR + MRP;         // Hessian NV*NV row-major (zeros for an LP)
     static constexpr int oF = oHs + NV * NV;     // f (16)
     static constexpr int oZ = oF + 16;           // z in/out (16)
     static constexpr int oRed = oZ + 16;         // reduction scratch / packed K / packed L (64)
     static constexpr int oOut = oRed + 64;       // [0] objective [1] iterations [2] flops (8)
     static constexpr int oLs = oOut + 8;         // packed Cholesky factor / working matrix (64)
     static constexpr int oD0 = oLs + 64;         // original diagonal of K (16)
-    static constexpr int oScr = oD0 + 16;        // 32 x 33 transposition scratch of the reductions
+    static constexpr int oHp = oD0 + 16;         // packed lower triangle of the Hessian (64)
+    static constexpr int oScr = oHp + 64;        // 32 x 33 transposition scratch of the reductions
     static constexpr int kDoubles = oScr + 32 * 33;
 };
 
@@ -147,8 +149,9 @@ struct IpmWs {
 constexpr int kScrStride = 33;
 
 // Sum CNT per-lane partials v[base .. base+CNT) over the warp into out[base .. base+CNT).
-template <int CNT, int P>
-__device__ __forceinline__ void reduce_round(const double (&v)[P], int base, double *out, double *scr, int lane)
+template <int CNT, int P, bool ADD = false>
+__device__ __forceinline__ void reduce_round(const double (&v)[P], int base, double *out, double *scr, int lane,
+                                             const double *add = nullptr)
 {
 #pragma unroll
     for (int i = 0; i < CNT; ++i) scr[i * kScrStride + lane] = v[base + i];
@@ -162,18 +165,22 @@ __device__ __forceinline__ void reduce_round(const double (&v)[P], int base, dou
         for (int j = 0; j < 8; ++j) t[j] += t[j + 8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) t[j] += t[j + 4];
-        out[base + lane] = (t[0] + t[2]) + (t[1] + t[3]);
+        const double sum = (t[0] + t[2]) + (t[1] + t[3]);
+        out[base + lane] = ADD ? sum + add[base + lane] : sum;
     }
     __syncwarp();
 }
 
 // Sum the first CNT of P per-lane partials over the warp into out[0..CNT) (shared memory).
-template <int CNT, int P>
-__device__ __forceinline__ void reduce_all(const double (&v)[P], double *out, double *scr, int lane)
+// With ADD the constant vector add[0..CNT) is added to the sums (the Hessian joins the normal
+// matrix here, two additions per lane instead of one per entry and lane later).
+template <int CNT, int P, bool ADD = false>
+__device__ __forceinline__ void reduce_all(const double (&v)[P], double *out, double *scr, int lane,
+                                           const double *add = nullptr)
 {
     constexpr int R0 = CNT < 32 ? CNT : 32;
-    reduce_round<R0>(v, 0, out, scr, lane);
-    if constexpr (CNT > 32) reduce_round<CNT - 32>(v, 32, out, scr, lane);
+    reduce_round<R0, P, ADD>(v, 0, out, scr, lane, add);
+    if constexpr (CNT > 32) reduce_round<CNT - 32, P, ADD>(v, 32, out, scr, lane, add);
 }
 
 // min over the warp of the fractions num/den (den > 0), compared by cross-multiplication so
@@ -210,9 +217,9 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
     constexpr int PV = 8 * ((NV + 7) / 8);
     const double *__restrict__ Gs = w + W::oG;
     const double *__restrict__ hs = w + W::oH;
-    double *sv = w + W::oS, *lv = w + W::oL, *av = w + W::oA, *bv = w + W::oB;
+    double *sv = w + W::oS, *lv = w + W::oL, *av = w + W::oA, *bv = w + W::oB, *rv = w + W::oR;
     const double *__restrict__ Hs = w + W::oHs;
-    double *red = w + W::oRed, *Ls = w + W::oLs, *D0 = w + W::oD0, *scr = w + W::oScr;
+    double *red = w + W::oRed, *Ls = w + W::oLs, *scr = w + W::oScr, *Hp = w + W::oHp;
     double z[NV], f[NV];
     double fmx = 0.0;
 #pragma unroll
@@ -222,6 +229,11 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         fmx = fmax(fmx, fabs(f[k]));
     }
     const double mact = warp_sum((double)__popc(act));
+    for (int idx = lane; idx < NK; idx += 32) {   // packed lower triangle of H
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+        Hp[idx] = Hs[i * NV + idx - i * (i + 1) / 2];
+    }
     // row pairs in which no lane has a participating row are skipped (warp-uniform)
     unsigned pairs = 0;
 #pragma unroll
@@ -300,7 +312,10 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
             const double rs0 = 1.0 / s0, rs1 = 1.0 / s1;
             av[r0] = rs0;
             if (on1) av[r1] = rs1;
-            rpm = fmax(rpm, fmax(m0 * fabs(gz0 + s0 - hs[r0]), m1 * fabs(gz1 + s1 - hs[r1])));
+            const double rp0 = gz0 + s0 - hs[r0], rp1 = gz1 + s1 - hs[r1];
+            rv[r0] = rp0;
+            if (on1) rv[r1] = rp1;
+            rpm = fmax(rpm, fmax(m0 * fabs(rp0), m1 * fabs(rp1)));
             mu = fma(s0, l0, fma(s1, l1, mu));
             lmx = fmax(lmx, fmax(l0, l1));
             const double wt0 = l0 * rs0, wt1 = l1 * rs1;
@@ -354,14 +369,14 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         // ---- K -> packed scratch -> Cholesky, redundantly in every lane's registers (SIMT makes
         //      the redundancy free; the lane-parallel shuffle version cost 1.5k instructions:
         //      a 64-bit shuffle is ~13 SASS instructions) -> packed factor in shared memory -----
-        reduce_all<NK>(acc, red, scr, lane);
+        reduce_all<NK, PK, true>(acc, red, scr, lane, Hp);
         double inv[NV];
         {
             double Lk[NK];
 #pragma unroll
             for (int i = 0; i < NV; ++i)
 #pragma unroll
-                for (int q = 0; q <= i; ++q) Lk[tri(i, q)] = red[tri(i, q)] + Hs[i * NV + q];
+                for (int q = 0; q <= i; ++q) Lk[tri(i, q)] = red[tri(i, q)];
             __syncwarp();
             bool bad = false;
 #pragma unroll
@@ -408,16 +423,14 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                 const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
                 const double m0 = (act >> j & 1u) ? 1.0 : 0.0;
                 const double m1 = (on1 && (act >> (j + 1) & 1u)) ? 1.0 : 0.0;
-                double g0[NV], g1[NV], gz0 = 0.0, gz1 = 0.0;
+                double g0[NV], g1[NV];
 #pragma unroll
                 for (int k = 0; k < NV; ++k) {
                     g0[k] = Gs[k * MRP + r0];
                     g1[k] = Gs[k * MRP + r1];
-                    gz0 = fma(g0[k], z[k], gz0);
-                    gz1 = fma(g1[k], z[k], gz1);
                 }
                 const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0], l1 = lv[r1];
-                const double rp0 = gz0 + s0 - hs[r0], rp1 = gz1 + s1 - hs[r1];
+                const double rp0 = rv[r0], rp1 = rv[r1];
                 // rc: s.lam (predictor) or s.lam + ds_aff.dl_aff - sigma mu (corrector)
                 const double rc0 = m0 * (s0 * l0 + (trip ? bv[r0] - sig * mu_mean : 0.0));
                 const double rc1 = m1 * (s1 * l1 + (trip ? bv[r1] - sig * mu_mean : 0.0));
@@ -459,17 +472,14 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                 const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
                 const double m1 = (on1 && (act >> (j + 1) & 1u)) ? 1.0 : 0.0;
                 const double m0 = (act >> j & 1u) ? 1.0 : 0.0;
-                double gz0 = 0.0, gz1 = 0.0, gd0 = 0.0, gd1 = 0.0;
+                double gd0 = 0.0, gd1 = 0.0;
 #pragma unroll
                 for (int k = 0; k < NV; ++k) {
-                    const double a0 = Gs[k * MRP + r0], a1 = Gs[k * MRP + r1];
-                    gz0 = fma(a0, z[k], gz0);
-                    gz1 = fma(a1, z[k], gz1);
-                    gd0 = fma(a0, dz[k], gd0);
-                    gd1 = fma(a1, dz[k], gd1);
+                    gd0 = fma(Gs[k * MRP + r0], dz[k], gd0);
+                    gd1 = fma(Gs[k * MRP + r1], dz[k], gd1);
                 }
                 const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0], l1 = lv[r1];
-                const double rp0 = gz0 + s0 - hs[r0], rp1 = gz1 + s1 - hs[r1];
+                const double rp0 = rv[r0], rp1 = rv[r1];
                 const double rc0 = trip ? bv[r0] : s0 * l0, rc1 = trip ? bv[r1] : s1 * l1;
                 const double ds0 = m0 * (-cres * rp0 - gd0), ds1 = m1 * (-cres * rp1 - gd1);
                 const double dl0 = m0 * (-rc0 - l0 * ds0) * av[r0], dl1 = m1 * (-rc1 - l1 * ds1) * av[r1];

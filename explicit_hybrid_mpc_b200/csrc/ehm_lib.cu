@@ -1,6 +1,7 @@
 // ehm_lib.cu -- problem object, candidate condensation and the batched oracle entry points
 // of libehm_b200.so (C-ABI in include/ehm.h).  sm_100a only; no CPU fallback: every entry
 // point fails with EHM_ECUDA when no CUDA device is usable.
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 
@@ -468,7 +469,7 @@ void fill_stats(ehm_partition *t, ehm_partition_stats *stats)
     stats->nnodes = h.nnodes; stats->nleaves = h.nleaves;
     stats->nsolves = (int64_t)(c1.solves - c0.solves); stats->niters = (int64_t)(c1.iters - c0.iters);
     stats->nfail = (int64_t)(c1.fails - c0.fails); stats->nwaves = t->waves; stats->nlaunches = t->launches;
-    stats->open_left = h.ftop + (h.necc_next - t->ecc_q0); stats->max_depth = h.max_depth;
+    stats->open_left = h.ftop + (h.necc_next - t->ecc_q0); stats->frontier = h.ftop; stats->max_depth = h.max_depth;
     stats->device_ms = t->device_ms;
     for (int k = 0; k < 8; ++k) { stats->stage_ms[k] = t->sms[k]; stats->stage_bytes[k] = t->sbytes[k]; stats->stage_flops[k] = 0; }
     stats->stage_flops[1] = c1.flops[1] - c0.flops[1]; stats->stage_flops[3] = c1.flops[2] - c0.flops[2];
@@ -476,8 +477,15 @@ void fill_stats(ehm_partition *t, ehm_partition_stats *stats)
 }
 
 template <int U, int NX, int MRI, int MRC>
-int advance_t(ehm_partition *t, int64_t max_waves)
+int advance_t(ehm_partition *t, int64_t max_waves, double budget_ms)
 {
+    // budget_ms > 0: stop after the first wave that ends past the budget (every wave ends with a
+    // stream synchronisation, so the host clock follows the device)
+    const auto t_in = std::chrono::steady_clock::now();
+    auto in_budget = [&]() {
+        return budget_ms <= 0.0 ||
+               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in).count() < budget_ms;
+    };
     ehm_problem *p = t->pb;
     const DevTables &tb = p->tb;
     const ehm_partition_opts &o = t->opts;
@@ -502,7 +510,7 @@ int advance_t(ehm_partition *t, int64_t max_waves)
     int64_t launches = 0, waves = 0;
     Ctl &h = t->hctl;
     // ---- ECC phase: roots (and their ECC descendants) -> L-CSS entries on the frontier ----
-    while (t->ecc_q0 < h.necc_next && h.error == 0 && (max_waves <= 0 || waves < max_waves)) {
+    while (t->ecc_q0 < h.necc_next && h.error == 0 && (max_waves <= 0 || waves < max_waves) && in_budget()) {
         const int q0 = t->ecc_q0;
         const int ne = std::min(kEccWave, h.necc_next - q0);
         EHM_CUDA(cudaEventRecord(sev[0], st));
@@ -523,7 +531,7 @@ int advance_t(ehm_partition *t, int64_t max_waves)
         if (o.verbose) fprintf(stderr, "[ehm] ecc wave: queue %d/%d frontier %d nodes %d\n", t->ecc_q0, h.necc_next, h.ftop, h.nnodes);
     }
     // ---- L-CSS phase ------------------------------------------------------------------------
-    while (h.ftop > 0 && h.error == 0 && (max_waves <= 0 || waves < max_waves)) {
+    while (h.ftop > 0 && h.error == 0 && (max_waves <= 0 || waves < max_waves) && in_budget()) {
         if (o.node_budget > 0 && h.nnodes >= o.node_budget) break;
         const int W = std::min(t->wv.W, h.ftop);
         const int base = h.ftop - W;
@@ -678,19 +686,25 @@ extern "C" int ehm_partition_set_root_ids(ehm_partition *t, int nroots, const in
     return EHM_OK;
 }
 
-extern "C" int ehm_partition_advance(ehm_partition *t, int64_t max_waves, ehm_partition_stats *stats)
+extern "C" int ehm_partition_advance_for(ehm_partition *t, int64_t max_waves, double budget_ms,
+                                         ehm_partition_stats *stats)
 {
     if (!t) return fail(EHM_EINVAL, "null partition");
     int rc;
     switch (t->pb->cfg) {
 #define X(ID, UU, NN, MM, CC) \
-    case ID: rc = advance_t<UU, NN, MM, CC>(t, max_waves); break;
+    case ID: rc = advance_t<UU, NN, MM, CC>(t, max_waves, budget_ms); break;
         EHM_FOR_EACH_CFG(X)
 #undef X
     default: rc = fail(EHM_EINVAL, "no kernel for this problem shape");
     }
     fill_stats(t, stats);
     return rc;
+}
+
+extern "C" int ehm_partition_advance(ehm_partition *t, int64_t max_waves, ehm_partition_stats *stats)
+{
+    return ehm_partition_advance_for(t, max_waves, 0.0, stats);
 }
 
 extern "C" int ehm_partition_run(ehm_problem *p, int nroots, const double *roots,

@@ -110,12 +110,15 @@ class _Engine:
             assert ids.shape[0] == roots.shape[0]
             _capi.check(self.L.ehm_partition_set_root_ids(self.h, roots.shape[0], ids.ctypes.data))
 
-    def advance(self, max_waves=0):
-        _capi.check(self.L.ehm_partition_advance(self.h, int(max_waves), C.byref(self.stats)))
+    def advance(self, max_waves=0, budget_ms=0.0):
+        _capi.check(self.L.ehm_partition_advance_for(self.h, int(max_waves), float(budget_ms),
+                                                     C.byref(self.stats)))
         return int(self.stats.open_left)
 
     def frontier_size(self):
-        return int(self.stats.open_left)
+        """frontier entries that :meth:`export` can hand over (root simplices still waiting for
+        their ECC pass are open work but not exportable)"""
+        return int(self.stats.frontier)
 
     def geom_width(self):
         n, nu = self.n, self.nu
@@ -131,6 +134,7 @@ class _Engine:
         _capi.check(self.L.ehm_partition_export(self.h, int(k), meta.data_ptr(), geom.data_ptr(),
                                                 lb.data_ptr()))
         self.stats.open_left -= k
+        self.stats.frontier -= k
         return meta, geom, lb
 
     def import_(self, meta, geom, lb, origin_rank):
@@ -142,6 +146,7 @@ class _Engine:
                                                 lb.contiguous().data_ptr(),
                                                 origin_rank.contiguous().data_ptr()))
         self.stats.open_left += k
+        self.stats.frontier += k
 
     def fetch(self, with_origin=False):
         nn, n, nu = int(self.stats.nnodes), self.n, self.nu
@@ -205,11 +210,13 @@ def shard_roots(roots, rank, world):
     return np.sort(order[rank::world])
 
 
-def rebalance_plan(sizes, fill, slack=1.5):
-    """Who sends how many frontier records to whom.  sizes: frontier depth per rank; fill: the
-    depth a rank needs to keep its GPU busy (one wave).  Returns an integer matrix send[i][j].
-    Nothing moves unless some rank is starving (depth < fill) while another holds more than
-    slack x the mean (and more than it needs itself).  Deterministic, identical on all ranks."""
+def rebalance_plan(sizes, fill, slack=2.0):
+    """Who sends how many frontier records to whom.  sizes: exportable frontier depth per rank;
+    fill: the depth a rank needs to keep its GPU busy.  Returns an integer matrix send[i][j].
+    Nothing moves unless some rank is starving (depth < fill and below the mean) while the
+    deepest frontier is more than slack x the shallowest; then every rank above the mean gives
+    its surplus (largest first) to the starving ranks, up to the mean.  Deterministic,
+    identical on all ranks."""
     sizes = np.asarray(sizes, dtype=np.int64)
     world = len(sizes)
     send = np.zeros((world, world), dtype=np.int64)
@@ -217,28 +224,23 @@ def rebalance_plan(sizes, fill, slack=1.5):
     if total == 0 or world == 1:
         return send
     mean = total / world
-    starving = sizes < min(fill, mean)
-    rich = (sizes > slack * mean) & (sizes > fill)
-    if not (starving.any() and rich.any()):
-        return send
     target = int(np.floor(mean))
-    surplus = np.maximum(sizes - max(target, 1), 0)
-    deficit = np.maximum(target - sizes, 0)
-    surplus[~rich] = 0
-    j = 0
+    starving = sizes < min(fill, mean)
+    if not starving.any() or sizes.max() <= slack * max(int(sizes.min()), 1) or target < 1:
+        return send
+    surplus = np.maximum(sizes - target, 0)
+    deficit = np.where(starving, np.maximum(target - sizes, 0), 0)
     for i in np.argsort(-surplus, kind='stable'):
         s = int(surplus[i])
-        while s > 0 and j < world:
-            order = np.argsort(-deficit, kind='stable')
-            r = int(order[0])
-            if deficit[r] <= 0:
+        for r in np.argsort(-deficit, kind='stable'):
+            if s <= 0:
                 break
             k = min(s, int(deficit[r]))
+            if k <= 0:
+                break
             send[i, r] += k
             s -= k
             deficit[r] -= k
-            j += 0
-        surplus[i] = s
     return send
 
 
@@ -281,14 +283,49 @@ def stitch(parts):
     return res
 
 
-def partition_distributed(oracle, roots, group=None, waves_per_round=2, wave=0, max_nodes=0,
+def deal_plan(sizes):
+    """The one-off shuffle that ends the ramp-up: every rank spreads ALL of its frontier records
+    evenly over all ranks (its own share included), so that each rank ends up with an
+    interleaved sample of every root's sub-trees.  send[i][j] = records rank i gives to rank j."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    world = len(sizes)
+    send = np.zeros((world, world), dtype=np.int64)
+    for i, k in enumerate(sizes):
+        # record e of rank i goes to rank (e + i) % world
+        dest = (np.arange(int(k)) + i) % world
+        send[i] = np.bincount(dest, minlength=world)
+    return send
+
+
+_CALLS = [0]
+
+
+def _default_store():
+    import torch.distributed as dist
+    try:
+        return dist.distributed_c10d._get_default_store()
+    except Exception:
+        return None
+
+
+def partition_distributed(oracle, roots, group=None, waves_per_round=1, wave=0, max_nodes=0,
                           max_frontier=0, verbose=0, engine_cls=_Engine, gather=True,
-                          fill_depth=512):
+                          fill_depth=256, round_ms=0.0, deal_depth=512, signal=True):
     """Partition ``roots`` with one process per GPU (see module docstring).
+
+    Every rank runs its own frontier loop on its share of the root simplices.  Ranks meet
+    (all-gather of two integers) only when one of them says so: a rank whose frontier falls
+    below ``fill_depth`` raises a flag in the process group's key-value store, the others see it
+    at their next wave boundary (``signal=True``; the device analogue of a reference worker
+    reporting idle, lib/worker.py:419-461).  At a meeting, frontier records move with
+    all-to-alls over NCCL: once as a full interleaved shuffle when the ramp-up has produced
+    ``deal_depth`` records per rank (:func:`deal_plan`), afterwards only from ranks holding a
+    surplus to starving ranks (:func:`rebalance_plan`).  With ``signal=False`` the ranks meet
+    every ``waves_per_round`` waves / ``round_ms`` milliseconds instead.
 
     Returns (PartitionResult or None, info): rank 0 gets the stitched result when ``gather``;
     ``info`` has the per-rank statistics needed by bench.py (leaves, device seconds, bytes
-    exchanged, number of rebalance rounds)."""
+    exchanged, number of exchange rounds)."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -296,24 +333,48 @@ def partition_distributed(oracle, roots, group=None, waves_per_round=2, wave=0, 
     roots = np.ascontiguousarray(roots, dtype=np.float64)
     mine = shard_roots(roots, rank, world)
     eng = engine_cls(oracle, roots[mine], wave, max_nodes, max_frontier, 0, verbose, root_ids=mine)
+    store = _default_store() if signal else None
+    _CALLS[0] += 1
+    prefix = 'ehm_b200/%d/' % _CALLS[0]
     fill = fill_depth
-    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-    rounds = moved = 0
+    sizes = torch.zeros(world, 2, dtype=torch.int64, device=dev)
+    rounds = meetings = moved = 0
+    dealt = world == 1
     xch_s = 0.0
     t0 = time.perf_counter()
     ev0 = ev1 = None
     if dev.type == 'cuda':
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(torch.cuda.default_stream(dev))
+
+    def frontier_of(e):
+        return e.frontier_size() if hasattr(e, 'frontier_size') else int(e.stats.open_left)
+
     try:
         while True:
-            mysize = eng.advance(waves_per_round)
-            me = torch.tensor([mysize], dtype=torch.int64, device=dev)
+            if store is not None:
+                key = prefix + str(meetings)
+                while True:
+                    mysize = eng.advance(waves_per_round)
+                    if mysize < fill or store.add(key, 0) > 0:
+                        break
+                store.add(key, 1)
+            elif round_ms > 0:
+                mysize = eng.advance(waves_per_round, round_ms)
+            else:
+                mysize = eng.advance(waves_per_round)
+            meetings += 1
+            me = torch.tensor([[mysize, frontier_of(eng)]], dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(sizes, me, group=group)
             sz = sizes.cpu().numpy()
-            if int(sz.sum()) == 0:
+            if int(sz[:, 0].sum()) == 0:
                 break
-            plan = rebalance_plan(sz, fill)
+            fr = sz[:, 1]
+            shuffle = False
+            if not dealt and int(fr.sum()) >= deal_depth * world and (sz[:, 0] == fr).all():
+                plan, dealt, shuffle = deal_plan(fr), True, True
+            else:
+                plan = rebalance_plan(fr, fill)
             if plan.sum() == 0:
                 continue
             tx = time.perf_counter()
@@ -323,6 +384,10 @@ def partition_distributed(oracle, roots, group=None, waves_per_round=2, wave=0, 
                 torch.empty(0, 6, dtype=torch.int32, device=dev),
                 torch.empty(0, eng.geom_width(), dtype=torch.float64, device=dev),
                 torch.empty(0, eng.ncand, dtype=torch.float32, device=dev))
+            if shuffle and k:
+                # interleave: record e goes to rank (e + rank) % world
+                order = torch.argsort((torch.arange(k, device=dev) + rank) % world, stable=True)
+                meta, geom, lb = meta[order].contiguous(), geom[order].contiguous(), lb[order].contiguous()
             nrecv = plan[:, rank]
             kr = int(nrecv.sum())
             rmeta = torch.empty(kr, 6, dtype=torch.int32, device=dev)
@@ -351,7 +416,7 @@ def partition_distributed(oracle, roots, group=None, waves_per_round=2, wave=0, 
         eng.close()
     wall = time.perf_counter() - t0
     info = dict(rank=rank, world=world, wall_s=wall, exchange_s=xch_s, rounds=rounds,
-                records_sent=moved, stats=st, loop_device_ms=loop_ms)
+                meetings=meetings, records_sent=moved, stats=st, loop_device_ms=loop_ms)
     result = None
     if gather:
         parts = [None] * world if rank == 0 else None

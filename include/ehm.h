@@ -103,7 +103,8 @@ typedef struct {
 
 typedef struct {
     int64_t nnodes, nleaves, nsolves, niters, nfail, nwaves, nlaunches;
-    int64_t open_left;     /* frontier entries left when a node_budget stopped the run      */
+    int64_t open_left;     /* open work left: frontier entries + root simplices still queued */
+    int64_t frontier;      /* of these, the entries ehm_partition_export can hand over      */
     int max_depth;
     double device_ms;      /* CUDA-event time of the whole loop                            */
     /* per pipeline stage, summed over waves (CUDA events on the launching stream):
@@ -126,6 +127,12 @@ int ehm_partition_create(ehm_problem *p, int nroots, const double *roots,
  * are inherited by all descendants and travel with exported records */
 int ehm_partition_set_root_ids(ehm_partition *t, int nroots, const int32_t *ids);
 int ehm_partition_advance(ehm_partition *t, int64_t max_waves, ehm_partition_stats *stats);
+/* the same with a time budget: returns after the first wave that ends more than budget_ms after
+ * the call (<= 0: no budget).  The multi-GPU driver uses it so that all ranks reach the
+ * depth exchange at about the same time (the reference's scheduler polls its workers every
+ * loop turn, lib/scheduler.py:425-441); the tree does not depend on where rounds end. */
+int ehm_partition_advance_for(ehm_partition *t, int64_t max_waves, double budget_ms,
+                              ehm_partition_stats *stats);
 /* Frontier exchange between ranks (replaces the worker->scheduler->worker task hand-over,
  * lib/worker.py:232-236, lib/scheduler.py:515-523).  export pops the k OLDEST entries into
  * caller-owned DEVICE buffers: d_meta int32[k][6] {node, cand, depth, root_id, skip, 0},

@@ -13,6 +13,14 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_deal_plan_is_an_even_interleave():
+    from explicit_hybrid_mpc_b200.partition import deal_plan
+    p = deal_plan([5, 3, 0, 1000])
+    assert (p.sum(axis=1) == [5, 3, 0, 1000]).all()
+    assert p.sum(axis=0).max() - p.sum(axis=0).min() <= 4       # every rank ends up with ~ total/world
+    assert (p[3] == 250).all() and list(p[0]) == [2, 1, 1, 1] and list(p[1]) == [0, 1, 1, 1]
+
+
 def test_rebalance_plan_properties():
     from explicit_hybrid_mpc_b200.partition import rebalance_plan
     rng = np.random.default_rng(0)
@@ -30,6 +38,9 @@ def test_rebalance_plan_properties():
             assert (after[plan.sum(axis=0) > 0] <= np.ceil(mean) + 1).all()
     assert rebalance_plan([5000, 4500, 4000, 4800], 512).sum() == 0      # balanced: nothing moves
     assert rebalance_plan([0, 0, 0], 512).sum() == 0
+    # one empty rank among full ones is served by everybody above the mean
+    p = rebalance_plan([0, 3000, 3200, 2900], 256)
+    assert p[:, 0].sum() == 2275 and (p[1:, 0] > 0).all()
     p = rebalance_plan([10000, 0, 50, 3000], 512)
     assert p[0].sum() > 6000 and p[1:].sum() == 0
 
@@ -115,7 +126,7 @@ class FakeEngine:
         pass
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, kw):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -125,7 +136,7 @@ def _worker(rank, world, port, q):
     nroots = 7
     roots = np.array([[[float(i)], [float(i) + 1.0 + 0.1 * i]] for i in range(nroots)])
     res, info = P.partition_distributed(oracle, roots, waves_per_round=1, engine_cls=FakeEngine,
-                                        fill_depth=3)
+                                        fill_depth=3, **kw)
     if rank == 0:
         q.put((dict(left=res.left, right=res.right, root_id=res.root_id, depth=res.depth,
                     closed=res.closed, vertices=res.vertices), info['rounds']))
@@ -133,14 +144,16 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_partition_distributed_gloo_world2():
+@pytest.mark.parametrize('kw', [dict(signal=True), dict(signal=True, deal_depth=2), dict(signal=False)],
+                         ids=['flagged', 'flagged+deal', 'fixed-rounds'])
+def test_partition_distributed_gloo_world2(kw):
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, kw)) for r in range(2)]
     for p in procs:
         p.start()
     out, rounds = q.get(timeout=120)

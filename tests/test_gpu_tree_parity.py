@@ -73,6 +73,30 @@ def test_tree_equals_cpu_oracle(sel, pendulum_roots, cpu_oracle, gpu_oracle):
     print('nodes %d leaves %d worst rel cost diff %.2e' % (res.nnodes, res.stats['nleaves'], worst))
 
 
+@pytest.mark.parametrize('base', [22, 0])
+def test_deep_config_tree_equals_cpu_oracle(base, pendulum, pendulum_roots):
+    """BASELINE config 3 (abs_frac 0.03 / eps_r 0.05, the reference's pairing table
+    post_process.py:334-338) on a depth-5 descendant of a root simplex: 1.5k / 50k nodes,
+    depth up to 21 below it."""
+    from explicit_hybrid_mpc_b200.oracle import Oracle
+    from explicit_hybrid_mpc_b200.partition import partition
+    from explicit_hybrid_mpc_b200.tools import split_along_longest_edge
+    from oracle.oracle_cpu import CpuOracle
+    eps_a, eps_r = 19.21220798973866 / 0.25 * 0.03, 0.05
+    R = pendulum_roots[base]
+    for d in range(5):
+        R = split_along_longest_edge(R)[d % 2]
+    gpu = Oracle(pendulum, eps_a, eps_r)
+    res = partition(gpu, R[None], wave=512)
+    assert res.stats['nfail'] == 0
+    cpu = CpuOracle(pendulum.problem, eps_a, eps_r, pendulum.theta_scale).partition(R[None], nthreads=8)
+    assert cpu['error'] == 0 and cpu['nfail'] == 0
+    assert res.stats['nleaves'] == cpu['nleaves'] and res.stats['nleaves'] > 500
+    worst = compare_trees(_gpu_arrays(res), cpu, 1)
+    print('deep: nodes %d leaves %d depth %d worst rel cost diff %.2e'
+          % (res.nnodes, res.stats['nleaves'], res.stats['max_depth'], worst))
+
+
 def test_cpu_prune_equals_bruteforce(pendulum_roots, cpu_oracle):
     """The inherited bounds only skip work: same tree with and without them (CPU oracle)."""
     roots = pendulum_roots[[22]]
