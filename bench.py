@@ -32,9 +32,9 @@ sys.path.insert(0, ROOT)
 ABS_FRAC, EPS_R = 0.25, 1.0
 EPS_A_FIXTURE = 19.21220798973866   # max_v P_theta(0.25 v).J, recomputed on the GPU at start-up
 METRIC = 'simplices partitioned/sec (eps-converged leaves)'
-# bounded CPU sample: the 6 cheapest root simplices of the workload (by leaf count); the CPU
-# oracle shares the work of ALL sampled roots over all threads (shared LIFO task queue)
-CPU_SAMPLE_ROOTS = None  # filled from tests/golden/pendulum_root_leafcounts.json when present
+# bounded CPU sample: the cheapest root simplices of the workload (by leaf count), as many as keep
+# the host threads busy for ~12 s; the CPU oracle shares the work of ALL sampled roots over all
+# threads (shared LIFO task queue)
 
 
 def _clock_sampler(stop, out, gpu_index):
@@ -69,13 +69,28 @@ def _roots():
     return np.load(os.path.join(ROOT, 'tests', 'golden', 'pendulum_roots.npy'))
 
 
-def _cpu_sample():
+def _cpu_sample(threads=None, seconds=12.0):
+    """Bounded sample of the workload for the CPU legs: the cheapest root simplices (by leaf
+    count of the committed full-size result) whose estimated work keeps `threads` host threads
+    busy for about `seconds`.  The rate comes from a calibration run on the two cheapest roots
+    (it under-estimates: the tree of two roots cannot feed many threads), hence the factor 2."""
     p = os.path.join(ROOT, 'tests', 'golden', 'pendulum_root_leafcounts.json')
-    if os.path.exists(p):
-        cnt = json.load(open(p))['leaves_per_root']
-        order = np.argsort(cnt)
-        return [int(i) for i in order[:6]]
-    return [22, 23, 24, 25]
+    if not os.path.exists(p):
+        return [22, 23, 24, 25]
+    meta = json.load(open(p))
+    cnt = meta['leaves_per_root']
+    order = [int(i) for i in np.argsort(cnt, kind='stable')]
+    if threads is None:
+        return order[:6]
+    cal = cpu_leg(threads, order[:2])
+    budget = 2.0 * cal['value'] * seconds          # leaves
+    sample, tot = [], 0
+    for i in order:
+        if len(sample) >= 6 and tot + cnt[i] > budget:
+            break
+        sample.append(i)
+        tot += cnt[i]
+    return sample
 
 
 def cpu_leg(threads, sample):
@@ -96,8 +111,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = _cpu_sample()
     threads = cores
+    sample = _cpu_sample(threads)
     vals, ms = [], []
     for i in range(args.warmup + args.steps):
         r = cpu_leg(threads, sample if i >= args.warmup else sample[:1])
@@ -114,7 +129,7 @@ def run_reference(args, rank, world):
                             note='CPU restatement of the reference algorithm (MOSEK/CVXPY/mpi4py '
                                  'not installable); bounded sample of root simplices %s' % sample),
                 cpu_baseline=dict(value=value, unit='leaves/s', cores=threads, kind='port',
-                                  sample='%d cheapest root simplices, %d leaves, %.1f s/step'
+                                  sample='%d cheapest root simplices (sized by a calibration run), %d leaves, %.1f s/step'
                                          % (len(sample), vals[-1]['leaves'], vals[-1]['seconds']),
                                   solves_per_s=sum(v['solves'] for v in vals) / secs),
                 e2e=dict(value=value, unit='leaves/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -227,9 +242,14 @@ def main():
     tot = torch.tensor([float(leaves), float(sum(r.stats['nsolves'] for r in results)),
                         float(launches)], dtype=torch.float64, device='cuda')
     mx = torch.tensor([sum(dev_ms) * 1e-3, sum(walls)], dtype=torch.float64, device='cuda')
+    busy = torch.tensor([results[-1].stats['device_ms']], dtype=torch.float64, device='cuda')
+    busy_all = torch.zeros(world, dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_gather_into_tensor(busy_all, busy)
+    else:
+        busy_all = busy
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -276,8 +296,8 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        sample = _cpu_sample()
         threads = os.cpu_count() or 1
+        sample = _cpu_sample(threads)
         c = cpu_leg(threads, sample)
         cpu = dict(value=c['value'], unit='leaves/s', cores=threads, kind='port',
                    sample='%d cheapest root simplices of the same workload (%d leaves, %.1f s)'
@@ -306,6 +326,7 @@ def main():
         gpu_launches=int(launches_all),
         clocks=_clocks_summary(samples),
         roofline=roofline, roofline_hbm=roofline_hbm, cpu_baseline=cpu,
+        rank_busy_ms_last_step=[round(x, 1) for x in busy_all.tolist()],
         wall_s_timed_region=t_total)
     print(json.dumps(line))
     if world > 1:

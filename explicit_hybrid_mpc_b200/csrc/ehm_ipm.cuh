@@ -59,6 +59,24 @@ __device__ __forceinline__ double warp_min(double v)
     return v;
 }
 
+// max / min over the warp of NON-NEGATIVE doubles (NaN propagates as the largest pattern): the
+// IEEE order of non-negative doubles is the unsigned order of their bit patterns, so two
+// 32-bit REDUX instructions replace a 5-level tree of 64-bit shuffles (~70 SASS instructions).
+__device__ __forceinline__ double warp_max_nonneg(double v)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(kFull, hi);
+    const unsigned ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ double warp_min_nonneg(double v)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(kFull, hi);
+    const unsigned ml = __reduce_min_sync(kFull, hi == mh ? lo : 0xffffffffu);
+    return __hiloint2double((int)mh, (int)ml);
+}
+
 __host__ __device__ constexpr int pow2_ge(int x) { return x <= 1 ? 1 : 2 * pow2_ge((x + 1) / 2); }
 
 // Recursive-halving reduce-scatter of P per-lane partials (P a power of two).  After the
@@ -207,13 +225,19 @@ __device__ __forceinline__ void warp_min_frac(double &num, double &den)
 // solver is latency bound with 7 resident warps per SM), are branch free (rows that do not
 // take part carry s = 1, lam = 0 and a zero mask) and contain no division: 1/s is formed once
 // per row and iteration, step-length ratios are compared by cross-multiplication.
+//
+// early (warp-uniform): the problem is a phase-1 LP  min sigma : G z - sigma <= h  (sigma = last
+// variable, started strictly feasible, so every iterate is a feasible point of it).  The solve
+// stops as soon as z_k leaves every original row a slack >= TAU_INT: "alive" is then certified
+// (sigma* <= -TAU_INT) and later iterations cannot change the answer (oracle/ehm_oracle.c:
+// qp_solve_x).  The objective returned in that case is the bound -TAU_INT.
 template <int NV, int MR>
-__device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
+__device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane, bool early = false)
 {
     using W = IpmWs<NV, MR>;
     constexpr int MRP = W::MRP;
     constexpr int NK = NV * (NV + 1) / 2;
-    constexpr int PK = 8 * ((NK + 7) / 8);   // accumulators padded to whole 8-value chunks
+    constexpr int PK = 8 * ((NK + 8) / 8);   // accumulators + the gap sum, padded to 8-value chunks
     constexpr int PV = 8 * ((NV + 7) / 8);
     const double *__restrict__ Gs = w + W::oG;
     const double *__restrict__ hs = w + W::oH;
@@ -234,6 +258,7 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         while ((i + 1) * (i + 2) / 2 <= idx) ++i;
         Hp[idx] = Hs[i * NV + idx - i * (i + 1) / 2];
     }
+    if (lane == 0) Hp[NK] = 0.0;   // slot of the gap sum s'lam in the reduction
     // row pairs in which no lane has a participating row are skipped (warp-uniform)
     unsigned pairs = 0;
 #pragma unroll
@@ -290,7 +315,10 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         double acc[PK];
 #pragma unroll
         for (int k = 0; k < PK; ++k) acc[k] = 0.0;
-        double mu = 0.0, rpm = 0.0, lmx = 0.0;
+        double rpm = 0.0, lmx = 0.0;
+        double &mu_acc = acc[NK];
+        bool cert = early;
+        const double cthr = EHM_TAU_INT + z[NV - 1];
 #pragma unroll 1
         for (int j = 0; j < MR; j += 2) {
             if (!(pairs >> j & 1u)) continue;
@@ -316,7 +344,9 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
             rv[r0] = rp0;
             if (on1) rv[r1] = rp1;
             rpm = fmax(rpm, fmax(m0 * fabs(rp0), m1 * fabs(rp1)));
-            mu = fma(s0, l0, fma(s1, l1, mu));
+            // slack of the original row (without the sigma column) at z_k: h - Gz - sigma_k
+            cert = cert && (m0 == 0.0 || s0 - rp0 >= cthr) && (m1 == 0.0 || s1 - rp1 >= cthr);
+            mu_acc = fma(s0, l0, fma(s1, l1, mu_acc));
             lmx = fmax(lmx, fmax(l0, l1));
             const double wt0 = l0 * rs0, wt1 = l1 * rs1;
 #pragma unroll
@@ -327,11 +357,15 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                     acc[tri(k, q)] = fma(gw0, g0[q], fma(gw1, g1[q], acc[tri(k, q)]));
             }
         }
-        mu = warp_sum(mu);
-        rpm = warp_max(rpm);
-        lmx = warp_max(lmx);
+        if (early && __all_sync(kFull, cert)) {
+            obj = -EHM_TAU_INT;
+            status = 0;
+            break;
+        }
+        rpm = warp_max_nonneg(rpm);
+        lmx = warp_max_nonneg(lmx);
         // (H z + f): lane k forms row k, exchanged through the scratch line
-        double hzf[NV];
+        double hzf[NV], zm;
         {
             if (lane < NV) {
                 double v = w[W::oF + lane];
@@ -340,7 +374,7 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                 red[lane] = v;
             }
             __syncwarp();
-            double zm = 0.0;
+            zm = 0.0;
             obj = 0.0;
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
@@ -349,6 +383,11 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                 zm = fmax(zm, fabs(z[k]));
             }
             __syncwarp();
+        }
+        // K (+H) and the gap sum -> red; Cholesky input stays there until it is loaded below
+        reduce_all<NK + 1, PK, true>(acc, red, scr, lane, Hp);
+        const double mu = red[NK];
+        {
             if (!isfinite(mu) || !isfinite(rpm) || !isfinite(obj)) {
                 status = 2;
                 break;
@@ -369,7 +408,6 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
         // ---- K -> packed scratch -> Cholesky, redundantly in every lane's registers (SIMT makes
         //      the redundancy free; the lane-parallel shuffle version cost 1.5k instructions:
         //      a 64-bit shuffle is ~13 SASS instructions) -> packed factor in shared memory -----
-        reduce_all<NK, PK, true>(acc, red, scr, lane, Hp);
         double inv[NV];
         {
             double Lk[NK];
@@ -499,8 +537,7 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane)
                     if (on1) bv[r1] = ds1 * dl1;
                 }
             }
-            warp_min_frac(an, ad);
-            const double amax = an / ad;
+            const double amax = warp_min_nonneg(an / ad);
             if (trip == 0) {
                 const double a_aff = fmin(1.0, amax);
                 sig = (1.0 - a_aff) * (1.0 - a_aff) * (1.0 - a_aff);

@@ -85,10 +85,11 @@ __device__ __forceinline__ unsigned act_of(int nrows, int lane)
 }
 
 template <int NV, int MRC>
-__device__ __forceinline__ int run_ipm(double *ws, unsigned act, int lane, SolveOut &out, double &obj)
+__device__ __forceinline__ int run_ipm(double *ws, unsigned act, int lane, SolveOut &out, double &obj,
+                                       bool early = false)
 {
     using W = IpmWs<NV, MRC>;
-    const int st = ipm_solve<NV, MRC>(ws, act, lane);
+    const int st = ipm_solve<NV, MRC>(ws, act, lane, early);
     obj = ws[W::oOut + 0];
     out.iters += (int)ws[W::oOut + 1];
     out.flops += ws[W::oOut + 2];
@@ -194,7 +195,7 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
     }
     __syncwarp();
     double obj;
-    int st = run_ipm<NV, MRC>(ws, act, lane, out, obj);
+    int st = run_ipm<NV, MRC>(ws, act, lane, out, obj, true);
     if (st != 0) {
         out.status = -1;
         return out;
@@ -402,7 +403,7 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
             zs[lane] = (lane == NB) ? s0 + 1.0 : 0.0;
         }
         __syncwarp();
-        const int st = run_ipm<NVS, MRC>(ws, act1, lane, out, obj);
+        const int st = run_ipm<NVS, MRC>(ws, act1, lane, out, obj, true);
         if (st != 0) {
             out.status = -1;
             return out;

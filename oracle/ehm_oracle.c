@@ -27,6 +27,16 @@
 
 static long g_iters = 0;
 long ehmo_total_iters(void) { return g_iters; }
+/* statistics of the decision solves (debugging aid, not thread-exact): phase-1 solves that
+ * ended alive / dead and their iterations, QP solves and their iterations */
+static long g_stat[6];
+void ehmo_stats(long *out) { for (int i = 0; i < 6; ++i) out[i] = g_stat[i]; }
+/* Early exit of the phase-1 LP (0 disables): the elastic LP starts strictly feasible, so every
+ * iterate (z_k, sigma_k) is a feasible point of it; as soon as z_k leaves all (normalised)
+ * slacks of the ORIGINAL rows >= TAU_INT the answer "alive" is certified (sigma* <= -TAU_INT)
+ * and the remaining iterations cannot change it. */
+static int g_early = 1;
+void ehmo_set_early_exit(int on) { g_early = on; }
 static inline double fmax2(double a, double b) { return a > b ? a : b; }
 
 struct ehmo_problem {
@@ -96,9 +106,21 @@ static void chol_solve(int nv, const double *L, double *b)
 /* z0 != NULL gives the primal start (slacks max(h-Gz0,1)).  returns 0 converged,        */
 /* 1 iteration limit, 2 factorisation breakdown.                                         */
 /* ------------------------------------------------------------------------------------ */
+static int qp_solve_x(int nv, int m, const double *H, const double *f, const double *G,
+                      const double *h, const double *z0, double *z, double *obj_out,
+                      int *iters_out, int early);
 static int qp_solve(int nv, int m, const double *H, const double *f, const double *G,
                     const double *h, const double *z0, double *z, double *obj_out,
                     int *iters_out)
+{
+    return qp_solve_x(nv, m, H, f, G, h, z0, z, obj_out, iters_out, 0);
+}
+
+/* early != 0: the problem is a phase-1 LP whose last variable is sigma with coefficient -1 in
+ * every row; stop as soon as the current z certifies sigma* <= -TAU_INT. */
+static int qp_solve_x(int nv, int m, const double *H, const double *f, const double *G,
+                      const double *h, const double *z0, double *z, double *obj_out,
+                      int *iters_out, int early)
 {
     double *s = dalloc(m), *lam = dalloc(m), *rp = dalloc(m), *ds = dalloc(m),
            *dl = dalloc(m), *rc = dalloc(m), *wv = dalloc(m);
@@ -124,12 +146,15 @@ static int qp_solve(int nv, int m, const double *H, const double *f, const doubl
             obj += z[j] * (f[j] + 0.5 * hz);
             rd[j] = v + hz;
         }
+        int cert = early;
         for (int r = 0; r < m; ++r) {
             double gz = 0;
             for (int j = 0; j < nv; ++j) {
                 gz += G[r * nv + j] * z[j];
                 rd[j] += G[r * nv + j] * lam[r];
             }
+            /* slack of the original row (without the sigma column) at z_k */
+            if (cert && !(h[r] - gz - z[nv - 1] >= EHMO_TAU_INT)) cert = 0;
             rp[r] = gz + s[r] - h[r];
             rpmax = fmax2(rpmax, fabs(rp[r]));
             mu += s[r] * lam[r];
@@ -143,6 +168,11 @@ static int qp_solve(int nv, int m, const double *H, const double *f, const doubl
         /* residuals relative to the magnitude of the terms they are made of (rows are
          * normalised, |G| <= 1): |Gz| <= |z|, |G'lam| <= |lam| */
         if (it == 0) rd0 = rdmax;
+        if (cert) {
+            obj = -EHMO_TAU_INT; /* certified: sigma* <= -TAU_INT */
+            status = 0;
+            break;
+        }
         /* Every step scales the dual residual by exactly (1 - alpha (1 - sigma)); the value
          * measured above additionally carries the round-off of the normal equations (up to
          * ~1e-4 relative once lam/s spans 20+ orders), so convergence is tested on the
@@ -306,12 +336,15 @@ static int phase1(ehmo_problem *pb, int nv, int m, const double *G, const double
     for (int j = 0; j < nv; ++j) { f[j] = 0; z0[j] = 0; }
     f[nv] = 1.0;
     z0[nv] = s0 + 1.0; /* strictly feasible start: slacks h+sigma >= 1 */
-    int st = qp_solve(na, m, NULL, f, Ga, h, z0, z, &obj, NULL);
+    int its = 0;
+    int st = qp_solve_x(na, m, NULL, f, Ga, h, z0, z, &obj, &its, sigma_out ? 0 : g_early);
     __sync_fetch_and_add(&pb->nsolves, 1);
     free(Ga);
     if (sigma_out) *sigma_out = obj;
     if (st != 0) return -1;
-    return obj <= -EHMO_TAU_INT ? 1 : 0;
+    const int alive = obj <= -EHMO_TAU_INT ? 1 : 0;
+    g_stat[alive ? 0 : 2]++; g_stat[alive ? 1 : 3] += its;
+    return alive;
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -665,7 +698,9 @@ static int solve_simplex_qp(ehmo_problem *pb, int c, const double *R, const doub
     double z[MAXNV], obj = 0;
     int mo = prep_rows(q.nv, q.m, q.G, q.h, q.rho, Gn, hn, pb->U, pb->n), st = 2;
     if (mo >= 0) {
-        st = qp_solve(q.nv, mo, q.H, q.f, Gn, hn, NULL, z, &obj, NULL);
+        int its = 0;
+        st = qp_solve(q.nv, mo, q.H, q.f, Gn, hn, NULL, z, &obj, &its);
+        g_stat[4]++; g_stat[5] += its;
         __sync_fetch_and_add(&pb->nsolves, 1);
     }
     if (st == 0) {

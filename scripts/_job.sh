@@ -1,3 +1,2 @@
-timeout 300 python -m pytest tests/test_gpu_distributed.py -x -q -m gpu 2>&1 | tail -60
-for w in 512 1024 2048; do timeout 120 python scripts/run_partition.py --wave $w 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('wave',$w,d['device_ms'],d['nwaves'],d['nleaves'],d['nfail'])"; done
-for cfg in "0 60" "1024 30"; do set -- $cfg; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 3 --wave $1 --round-ms $2 2>&1 | tail -1 | tee gpurun_out/bench_n2_w$1_r$2.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('N2 wave',$1,'round',$2,d['ms_per_step'],d['value'],d['e2e']['value'],d['config']['parallelism'][-60:])"; done
+timeout 900 python -m pytest tests/test_gpu_batch_parity.py tests/test_gpu_tree_parity.py -x -q -m gpu 2>&1 | tail -5
+timeout 200 python scripts/run_partition.py 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('v9',d['device_ms'],d['nwaves'],d['nleaves'],d['nfail'],d['iters_per_solve'],d['nsolves'])"
