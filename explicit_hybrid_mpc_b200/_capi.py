@@ -22,7 +22,8 @@ EXPORTS = [
     'ehm_last_error', 'ehm_kernel_launches', 'ehm_qp_theta_delta_batch', 'ehm_simplex_batch',
     'ehm_split_batch', 'ehm_partition_run', 'ehm_partition_fetch', 'ehm_partition_free',
     'ehm_read_counters', 'ehm_fp64_peak', 'ehm_hbm_peak', 'ehm_partition_create',
-    'ehm_partition_advance', 'ehm_partition_advance_for', 'ehm_partition_export', 'ehm_partition_import',
+    'ehm_partition_advance', 'ehm_partition_advance_for', 'ehm_locator_create', 'ehm_locator_eval',
+    'ehm_locator_destroy', 'ehm_partition_export', 'ehm_partition_import',
     'ehm_partition_fetch_origin', 'ehm_partition_set_root_ids', 'ehm_last_failure',
     'ehm_debug_trace', 'ehm_debug_fetch',
 ]
@@ -88,6 +89,10 @@ def lib():
                                                C.POINTER(PartitionOpts), C.POINTER(vp)]
             L.ehm_partition_advance.argtypes = [vp, C.c_int64, C.POINTER(PartitionStats)]
             L.ehm_partition_advance_for.argtypes = [vp, C.c_int64, C.c_double, C.POINTER(PartitionStats)]
+            L.ehm_locator_create.argtypes = [C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_int32,
+                                             C.POINTER(C.c_void_p)]
+            L.ehm_locator_eval.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+            L.ehm_locator_destroy.argtypes = [vp]
             L.ehm_partition_export.argtypes = [vp, C.c_int, vp, vp, vp]
             L.ehm_partition_import.argtypes = [vp, C.c_int, vp, vp, vp, vp]
             L.ehm_partition_fetch_origin.argtypes = [vp, vp]

@@ -424,6 +424,7 @@ extern "C" int ehm_read_counters(ehm_problem *p, int64_t *iters, int64_t *solves
 // partition engine (host side)
 // =========================================================================================
 #include "ehm_partition.cuh"
+#include "ehm_locate.cuh"
 
 struct ehm_partition {
     ehm_problem *pb = nullptr;
@@ -949,5 +950,74 @@ extern "C" int ehm_debug_trace(int on)
 extern "C" int ehm_debug_fetch(double *out)
 {
     EHM_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(double) * 8 * 128));
+    return EHM_OK;
+}
+
+
+// ---- online evaluation of the explicit control law (lib/mpc_library.py:662-792) ------------
+struct ehm_locator {
+    ehm::LocTree t{};
+    int *left = nullptr, *right = nullptr;
+    double *cm = nullptr, *vinput = nullptr;
+};
+
+extern "C" int ehm_locator_destroy(ehm_locator *l)
+{
+    if (!l) return EHM_OK;
+    cudaFree(l->left); cudaFree(l->right); cudaFree(l->cm); cudaFree(l->vinput);
+    delete l;
+    return EHM_OK;
+}
+
+extern "C" int ehm_locator_create(int n, int nu, int64_t nnodes, const int32_t *left, const int32_t *right,
+                                  const double *vertices, const double *vinput, int32_t top, ehm_locator **out)
+{
+    if (!out || n < 1 || n > ehm::kLocMaxN || nu < 1 || nnodes < 1 || !left || !right || !vertices || !vinput ||
+        top < 0 || top >= nnodes)
+        return fail(EHM_EINVAL, "bad argument");
+    *out = nullptr;
+    ehm_locator *l = new ehm_locator();
+    double *dv = nullptr;
+    const size_t nv = (size_t)nnodes * (n + 1) * n, nc = (size_t)nnodes * (n + n * n),
+                 ni = (size_t)nnodes * (n + 1) * nu;
+    cudaError_t e = cudaMalloc(&l->left, nnodes * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&l->right, nnodes * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&l->cm, nc * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&l->vinput, ni * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&dv, nv * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(l->left, left, nnodes * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(l->right, right, nnodes * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(l->vinput, vinput, ni * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dv, vertices, nv * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        ehm::k_loc_prepare<<<(unsigned)((nnodes + 127) / 128), 128>>>(n, nnodes, dv, l->cm);
+        g_launches += 1;
+        e = cudaDeviceSynchronize();
+    }
+    cudaFree(dv);
+    if (e != cudaSuccess) {
+        ehm_locator_destroy(l);
+        return fail(EHM_ECUDA, std::string("locator: ") + cudaGetErrorString(e));
+    }
+    l->t.n = n; l->t.nu = nu; l->t.top = top; l->t.nnodes = nnodes;
+    l->t.left = l->left; l->t.right = l->right; l->t.cm = l->cm; l->t.vinput = l->vinput;
+    *out = l;
+    return EHM_OK;
+}
+
+extern "C" int ehm_locator_eval(ehm_locator *l, int64_t B, const double *d_theta, double *d_u, int32_t *d_leaf,
+                                cudaStream_t stream)
+{
+    if (!l || B < 0 || (B > 0 && (!d_theta || !d_u))) return fail(EHM_EINVAL, "bad argument");
+    if (B == 0) return EHM_OK;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    switch (l->t.n) {
+#define X(NN) case NN: ehm::k_locate<NN><<<grid, 128, 0, stream>>>(l->t, B, d_theta, d_u, d_leaf); break;
+        X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#undef X
+    default: return fail(EHM_EINVAL, "unsupported dimension");
+    }
+    g_launches += 1;
+    EHM_CUDA(cudaGetLastError());
     return EHM_OK;
 }

@@ -256,3 +256,7 @@ class SyntheticMPLP:
             C=-S, D=A, e=b, Q=np.zeros((n, n)), P=np.zeros((n, n)),
             R=np.zeros((nz, nz)), ru=c, u_scale=np.ones(nz), name='synthetic_mplp',
             meta=dict(seed=seed)).validate()
+
+
+# name parity with the reference, where ExplicitMPC lives in lib/mpc_library.py:662-792
+from .explicit_mpc import ExplicitMPC  # noqa: E402,F401

@@ -171,6 +171,20 @@ int ehm_fp64_peak(double *tflops);
 /* STREAM-style device copy of `bytes` bytes: GB/s (read+write counted) */
 int ehm_hbm_peak(int64_t bytes, double *gbs);
 
+/* ---- online evaluation of the explicit control law --------------------------------------
+ * ExplicitMPC (lib/mpc_library.py:662-792): compute_simplex_basis_inverse (:684-712) =
+ * ehm_locator_create (Minv of every node, on the device); get_containing_cell +
+ * __call__ (:738-792) = ehm_locator_eval for a batch of B parameters.  The tree is the FULL
+ * tree (triangulation spine included) as flat HOST arrays: left/right child ids (-1 = leaf),
+ * vertices (nnodes,(n+1),n), vertex inputs (nnodes,(n+1),nu); `top` = id of the tree root.
+ * d_theta (B,n), d_u (B,nu), d_leaf (B, optional) are DEVICE pointers. */
+typedef struct ehm_locator ehm_locator;
+int ehm_locator_create(int n, int nu, int64_t nnodes, const int32_t *left, const int32_t *right,
+                       const double *vertices, const double *vinput, int32_t top, ehm_locator **out);
+int ehm_locator_eval(ehm_locator *l, int64_t B, const double *d_theta, double *d_u, int32_t *d_leaf,
+                     cudaStream_t stream);
+int ehm_locator_destroy(ehm_locator *l);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,9 @@ ehmo_problem *ehmo_create(int n, int nu, int N, int K, int p,
 void ehmo_destroy(ehmo_problem *pb);
 void ehmo_set_eps(ehmo_problem *pb, double eps_a, double eps_r);
 void ehmo_set_presolve(int on); /* 1 (default): drop rows that cannot bind in the input box */
+void ehmo_set_early_exit(int on); /* 1 (default): stop a phase-1 LP at the first certified interior point */
+void ehmo_stats(long *out6);      /* phase-1 alive / its, phase-1 dead / its, QP solves / its */
+long ehmo_total_iters(void);
 int ehmo_num_candidates(const ehmo_problem *pb);
 long ehmo_solve_count(const ehmo_problem *pb); /* convex sub-problems solved so far */
 

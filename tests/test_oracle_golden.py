@@ -99,3 +99,26 @@ def test_row_presolve_is_exact(pendulum, pendulum_roots, cpu_oracle):
     pre = cpu_oracle.partition(roots, nthreads=4)
     assert full['nfail'] == 0 and pre['nfail'] == 0
     assert compare_trees(pre, full, 1) <= 1e-6
+
+
+def test_phase1_early_exit_is_exact(pendulum_roots, cpu_oracle):
+    """Stopping a phase-1 LP at the first iterate that certifies an interior point (DESIGN.md
+    "Phase-1 early exit") must not change any decision: identical tree, fewer iterations."""
+    import ctypes as C
+    from oracle.oracle_cpu import lib
+    from test_gpu_tree_parity import compare_trees
+    L = lib()
+    L.ehmo_total_iters.restype = C.c_long
+    roots = pendulum_roots[[22]]
+    try:
+        L.ehmo_set_early_exit(0)
+        i0 = L.ehmo_total_iters()
+        full = cpu_oracle.partition(roots, nthreads=4)
+        i1 = L.ehmo_total_iters()
+    finally:
+        L.ehmo_set_early_exit(1)
+    early = cpu_oracle.partition(roots, nthreads=4)
+    i2 = L.ehmo_total_iters()
+    assert full['nfail'] == 0 and early['nfail'] == 0 and full['nsolves'] == early['nsolves']
+    assert compare_trees(early, full, 1) <= 1e-9
+    assert (i2 - i1) < 0.85 * (i1 - i0)
