@@ -72,8 +72,8 @@ def _roots():
 def _cpu_sample(threads=None, seconds=12.0):
     """Bounded sample of the workload for the CPU legs: the cheapest root simplices (by leaf
     count of the committed full-size result) whose estimated work keeps `threads` host threads
-    busy for about `seconds`.  The rate comes from a calibration run on the two cheapest roots
-    (it under-estimates: the tree of two roots cannot feed many threads), hence the factor 2."""
+    busy for about `seconds`.  The rate comes from a calibration run on the four cheapest roots
+    (it under-estimates: their small trees cannot feed many threads for long), hence the 1.5."""
     p = os.path.join(ROOT, 'tests', 'golden', 'pendulum_root_leafcounts.json')
     if not os.path.exists(p):
         return [22, 23, 24, 25]
@@ -82,8 +82,8 @@ def _cpu_sample(threads=None, seconds=12.0):
     order = [int(i) for i in np.argsort(cnt, kind='stable')]
     if threads is None:
         return order[:6]
-    cal = cpu_leg(threads, order[:2])
-    budget = 2.0 * cal['value'] * seconds          # leaves
+    cal = cpu_leg(threads, order[:4])
+    budget = 1.5 * cal['value'] * seconds          # leaves
     sample, tot = [], 0
     for i in order:
         if len(sample) >= 6 and tot + cnt[i] > budget:

@@ -26,11 +26,21 @@
 #define MAXNV 40
 
 static long g_iters = 0;
-long ehmo_total_iters(void) { return g_iters; }
+/* Counters are accumulated per thread and flushed once per task / API call: a shared counter
+ * bumped in every IPM iteration turns into a cache line bouncing between all cores (it capped
+ * the 128-thread host of the GPU box at the throughput of 8 cores). */
+static __thread long t_iters = 0, t_solves = 0, t_stat[6] = {0, 0, 0, 0, 0, 0};
+static int env_flag(const char *name, int *cache)
+{
+    if (*cache < 0) *cache = getenv(name) != NULL;
+    return *cache;
+}
+static int dbg_debug = -1, dbg_failtrace = -1, dbg_trace = -1;
+long ehmo_total_iters(void) { return g_iters + t_iters; }
 /* statistics of the decision solves (debugging aid, not thread-exact): phase-1 solves that
  * ended alive / dead and their iterations, QP solves and their iterations */
 static long g_stat[6];
-void ehmo_stats(long *out) { for (int i = 0; i < 6; ++i) out[i] = g_stat[i]; }
+void ehmo_stats(long *out) { for (int i = 0; i < 6; ++i) out[i] = g_stat[i] + t_stat[i]; }
 /* Early exit of the phase-1 LP (0 disables): the elastic LP starts strictly feasible, so every
  * iterate (z_k, sigma_k) is a feasible point of it; as soon as z_k leaves all (normalised)
  * slacks of the ORIGINAL rows >= TAU_INT the answer "alive" is certified (sigma* <= -TAU_INT)
@@ -164,7 +174,7 @@ static int qp_solve_x(int nv, int m, const double *H, const double *f, const dou
         for (int j = 0; j < nv; ++j) zmax = fmax2(zmax, fabs(z[j]));
         for (int r = 0; r < m; ++r) lmax = fmax2(lmax, lam[r]);
         if (!isfinite(mu) || !isfinite(rdmax) || !isfinite(rpmax)) { status = 2; break; }
-        if (getenv("EHMO_DEBUG")) fprintf(stderr, "it %d rp %.3e rd %.3e mu %.3e obj %.10g lmax %.3e zmax %.3e\n", it, rpmax, rdmax, mu, obj, lmax, zmax);
+        if (env_flag("EHMO_DEBUG", &dbg_debug)) fprintf(stderr, "it %d rp %.3e rd %.3e mu %.3e obj %.10g lmax %.3e zmax %.3e\n", it, rpmax, rdmax, mu, obj, lmax, zmax);
         /* residuals relative to the magnitude of the terms they are made of (rows are
          * normalised, |G| <= 1): |Gz| <= |z|, |G'lam| <= |lam| */
         if (it == 0) rd0 = rdmax;
@@ -249,9 +259,9 @@ static int qp_solve_x(int nv, int m, const double *H, const double *f, const dou
                 }
             }
         }
-        g_iters++;
+        t_iters++;
         rho *= 1.0 - alpha * resc;
-        if (getenv("EHMO_DEBUG")) {
+        if (env_flag("EHMO_DEBUG", &dbg_debug)) {
             double mn = 1e300, mx = 0; int imn = -1;
             for (int r = 0; r < m; ++r) { double pr = s[r] * lam[r]; if (pr < mn) { mn = pr; imn = r; } if (pr > mx) mx = pr; }
             fprintf(stderr, "    alpha %.3e  min s.lam %.3e (row %d s %.3e lam %.3e) max %.3e mu %.3e\n", alpha, mn, imn, s[imn], lam[imn], mx, mu);
@@ -263,7 +273,7 @@ static int qp_solve_x(int nv, int m, const double *H, const double *f, const dou
         }
     }
     *obj_out = obj;
-    if (status != 0 && getenv("EHMO_FAILTRACE")) {
+    if (status != 0 && env_flag("EHMO_FAILTRACE", &dbg_failtrace)) {
         double rpm = 0, rdm = 0, mu = 0;
         for (int r = 0; r < m; ++r) { rpm = fmax2(rpm, fabs(rp[r])); mu += s[r] * lam[r]; }
         for (int j = 0; j < nv; ++j) rdm = fmax2(rdm, fabs(rd[j]));
@@ -324,6 +334,7 @@ static int prep_rows(int nv, int m, const double *G, const double *h, const doub
 static int phase1(ehmo_problem *pb, int nv, int m, const double *G, const double *h,
                   double *sigma_out)
 {
+    (void)pb;
     int na = nv + 1;
     double *Ga = dalloc((size_t)m * na);
     double f[MAXNV], z0[MAXNV], z[MAXNV], obj;
@@ -338,12 +349,12 @@ static int phase1(ehmo_problem *pb, int nv, int m, const double *G, const double
     z0[nv] = s0 + 1.0; /* strictly feasible start: slacks h+sigma >= 1 */
     int its = 0;
     int st = qp_solve_x(na, m, NULL, f, Ga, h, z0, z, &obj, &its, sigma_out ? 0 : g_early);
-    __sync_fetch_and_add(&pb->nsolves, 1);
+    t_solves++;
     free(Ga);
     if (sigma_out) *sigma_out = obj;
     if (st != 0) return -1;
     const int alive = obj <= -EHMO_TAU_INT ? 1 : 0;
-    g_stat[alive ? 0 : 2]++; g_stat[alive ? 1 : 3] += its;
+    t_stat[alive ? 0 : 2]++; t_stat[alive ? 1 : 3] += its;
     return alive;
 }
 
@@ -470,7 +481,18 @@ void ehmo_set_eps(ehmo_problem *pb, double eps_a, double eps_r)
     pb->eps_r = eps_r;
 }
 int ehmo_num_candidates(const ehmo_problem *pb) { return pb->ncand; }
-long ehmo_solve_count(const ehmo_problem *pb) { return pb->nsolves; }
+static void flush_thread_counters(ehmo_problem *pb)
+{
+    if (t_solves) { __sync_fetch_and_add(&pb->nsolves, t_solves); t_solves = 0; }
+    if (t_iters) { __sync_fetch_and_add(&g_iters, t_iters); t_iters = 0; }
+    for (int i = 0; i < 6; ++i)
+        if (t_stat[i]) { __sync_fetch_and_add(&g_stat[i], t_stat[i]); t_stat[i] = 0; }
+}
+long ehmo_solve_count(const ehmo_problem *pb)
+{
+    flush_thread_counters((ehmo_problem *)pb);
+    return pb->nsolves;
+}
 
 /* ------------------------------------------------------------------------------------ */
 /* P_theta_delta (lib/oracle.py:141-173): fixed-commutation convex QP at one theta.       */
@@ -514,7 +536,7 @@ int ehmo_p_theta_delta(ehmo_problem *pb, const double *theta, int c, double *J, 
             }
             int st = qp_solve(U, mo, H, f, Gn, hn, NULL, z, &obj, NULL);
             obj *= cs;
-            __sync_fetch_and_add(&pb->nsolves, 1);
+            t_solves++;
             if (st == 0) {
                 ret = 1;
                 if (J) *J = obj + cst;
@@ -700,8 +722,8 @@ static int solve_simplex_qp(ehmo_problem *pb, int c, const double *R, const doub
     if (mo >= 0) {
         int its = 0;
         st = qp_solve(q.nv, mo, q.H, q.f, Gn, hn, NULL, z, &obj, &its);
-        g_stat[4]++; g_stat[5] += its;
-        __sync_fetch_and_add(&pb->nsolves, 1);
+        t_stat[4]++; t_stat[5] += its;
+        t_solves++;
     }
     if (st == 0) {
         *val = q.cs * obj + q.cst;
@@ -709,7 +731,7 @@ static int solve_simplex_qp(ehmo_problem *pb, int c, const double *R, const doub
             memcpy(zsol, z, sizeof(double) * q.nv);
             if (with_tau) zsol[q.nv - 1] *= q.cs;
         }
-    } else if (getenv("EHMO_FAILTRACE")) {
+    } else if (env_flag("EHMO_FAILTRACE", &dbg_failtrace)) {
         fprintf(stderr, "SIMPLEXFAIL c %d tau %d R", c, with_tau);
         for (int i = 0; i < (pb->n + 1) * pb->n; ++i) fprintf(stderr, " %.17g", R[i]);
         fprintf(stderr, " Vr");
@@ -1026,7 +1048,7 @@ static void lcss_step(builder *b, long id, double *lb)
     ehmo_lcss_result res;
     ehmo_lcss_eval(pb, R, Vr, cref, lb, b->prune, th, Jn, Un, &res);
     __sync_fetch_and_add(&t->nfail, res.n_fail);
-    if (getenv("EHMO_TRACE"))
+    if (env_flag("EHMO_TRACE", &dbg_trace))
         fprintf(stderr, "node %ld depth %d cref %d evaluated %d tref %.4g conv %d cstar %d vs %d\n",
                 id, t->depth[id], cref, res.n_eval, res.t_ref, res.converged, res.cstar, res.var_small);
     if (res.converged) { /* worker.py:368-375 close leaf */
@@ -1095,6 +1117,7 @@ static void *thread_main(void *p)
             else ecc_step(b, k->id);
         } else free(k->lb);
         free(k);
+        flush_thread_counters(b->pb);
         pthread_mutex_lock(&b->mu);
         b->busy--;
         if (b->t.error) b->stop = 1;
