@@ -65,6 +65,26 @@ def _clocks_summary(samples):
                 samples=len(samples))
 
 
+def _host_cores():
+    """Host threads this process can really use: the affinity mask, capped by the cgroup CPU
+    quota (the GPU boxes report 128 CPUs but run under a 16-CPU quota; more threads than the
+    quota only adds contention: 16 threads 554k solves/s, 128 threads 337k)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q[0] != 'max':
+            n = min(n, max(1, int(float(q[0]) / float(q[1]) + 0.5)))
+    except Exception:
+        try:
+            quota = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            period = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if quota > 0:
+                n = min(n, max(1, int(quota / period + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 def _roots():
     return np.load(os.path.join(ROOT, 'tests', 'golden', 'pendulum_roots.npy'))
 
@@ -110,8 +130,7 @@ def cpu_leg(threads, sample):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    threads = cores
+    threads = _host_cores()
     sample = _cpu_sample(threads)
     vals, ms = [], []
     for i in range(args.warmup + args.steps):
@@ -280,9 +299,18 @@ def main():
     solve_ms = sm[1] + sm[3] + sm[5] + sm[7]
     solve_fl = st['stage_flops'][1] + st['stage_flops'][3] + st['stage_flops'][5] + st['stage_flops'][7]
     ach = st['stage_flops'][3] / (sm[3] * 1e-3) / 1e12 if sm[3] > 0 else 0.0
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, 'profiles', 'r1_final_traffic.json')
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
+        except Exception:
+            pass
     roofline = dict(bound='fp64', kernel='k_lcss_eval (warp-per-problem IPM)', achieved=ach,
                     peak=pk.value, unit='TFLOP/s', frac=ach / pk.value if pk.value else None,
-                    traffic=None,
+                    traffic=traffic, traffic_unit='dram bytes of ONE saturated launch (not per step)',
+                    traffic_source=traffic_src,
                     note='fp64 FMA-pipe bound (SURVEY 8d): peak = in-run DFMA microbenchmark '
                          '(ehm_fp64_peak); achieved = algorithmic flops of all k_lcss_eval launches '
                          'of the last step / their summed CUDA-event time; all IPM kernels together: '
@@ -296,7 +324,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
+        threads = _host_cores()
         sample = _cpu_sample(threads)
         c = cpu_leg(threads, sample)
         cpu = dict(value=c['value'], unit='leaves/s', cores=threads, kind='port',

@@ -200,6 +200,60 @@ def partition(oracle, roots, wave=0, max_nodes=0, max_frontier=0, node_budget=0,
     return PartitionResult(arr, st, oracle.pb)
 
 
+def partition_checkpoint(oracle, roots, path, node_budget, wave=0, max_nodes=0, max_frontier=0,
+                         verbose=0):
+    """Run the partition until about ``node_budget`` nodes exist, then write a checkpoint
+    (``.npz``): the node store so far and every open frontier record (geometry, vertex costs
+    and inputs, certified per-candidate bounds).  The reference checkpoints by pickling
+    ``tree.pkl`` / ``branch_*.pkl`` and re-queueing unfinished leaves on restart
+    (``lib/scheduler.py:388-391,620-642``).  Returns the number of open records (0 = the run
+    finished and the checkpoint holds the complete tree)."""
+    roots = np.ascontiguousarray(roots, dtype=np.float64)
+    eng = _Engine(oracle, roots, wave, max_nodes, max_frontier, node_budget, verbose)
+    try:
+        left = eng.advance(0)
+        while left > eng.frontier_size():          # root simplices still waiting for their ECC pass
+            left = eng.advance(1)
+        k = eng.frontier_size()
+        meta, geom, lb = eng.export(k) if k else (None, None, None)
+        arr = eng.fetch(with_origin=True)
+        st = eng.stats_dict()
+    finally:
+        eng.close()
+    out = {('node_' + f): arr[f] for f in arr}
+    if k:
+        out.update(meta=meta.cpu().numpy(), geom=geom.cpu().numpy(), lb=lb.cpu().numpy())
+    out['open'] = np.int64(k)
+    out['nleaves'] = np.int64(st['nleaves'])
+    np.savez_compressed(path, **out)
+    return k
+
+
+def partition_resume(oracle, path, wave=0, max_nodes=0, max_frontier=0, verbose=0):
+    """Continue a :func:`partition_checkpoint` to convergence; returns the complete
+    :class:`PartitionResult` (identical to an uninterrupted run)."""
+    import torch
+    z = np.load(path)
+    first = {f[5:]: z[f] for f in z.files if f.startswith('node_')}
+    k = int(z['open'])
+    if k == 0:
+        merged = stitch([first])
+        return PartitionResult(merged, dict(nleaves=int(z['nleaves'])), oracle.pb)
+    dev = oracle.device
+    eng = _Engine(oracle, np.zeros((0, oracle.n + 1, oracle.n)), wave, max_nodes, max_frontier, 0, verbose)
+    try:
+        eng.import_(torch.as_tensor(z['meta'], device=dev), torch.as_tensor(z['geom'], device=dev),
+                    torch.as_tensor(z['lb'], device=dev),
+                    torch.zeros(k, dtype=torch.int32, device=dev))       # origin "rank" 0 = the checkpoint
+        eng.advance(0)
+        second = eng.fetch(with_origin=True)
+        st = eng.stats_dict()
+    finally:
+        eng.close()
+    st['nleaves'] = int(st['nleaves']) + int(z['nleaves'])
+    return PartitionResult(stitch([first, second]), st, oracle.pb)
+
+
 # --------------------------------------------------------------------------------------------
 # multi-GPU: sharded frontier + all-to-all rebalance
 # --------------------------------------------------------------------------------------------

@@ -138,3 +138,16 @@ def test_full_partition_invariants(pendulum, pendulum_roots, gpu_oracle):
     J, _, st = gpu_oracle.point_batch(th, cd)
     assert (st.cpu().numpy() == 1).all()
     assert np.allclose(J.cpu().numpy(), res.vcost[samp].reshape(-1), rtol=1e-7, atol=1e-7)
+
+
+def test_checkpoint_resume_equals_uninterrupted(tmp_path, pendulum_roots, gpu_oracle):
+    """Stop after ~300 nodes, write the checkpoint, resume in a fresh engine: same forest."""
+    from explicit_hybrid_mpc_b200.partition import partition, partition_checkpoint, partition_resume
+    roots = pendulum_roots[[22, 44]]
+    path = str(tmp_path / 'ckpt.npz')
+    left = partition_checkpoint(gpu_oracle, roots, path, node_budget=300, wave=32)
+    assert left > 0
+    res = partition_resume(gpu_oracle, path, wave=64)
+    full = partition(gpu_oracle, roots)
+    assert res.stats['nleaves'] == full.stats['nleaves'] and res.nnodes == full.nnodes
+    compare_trees(_gpu_arrays(res), _gpu_arrays(full), 2)
