@@ -635,7 +635,7 @@ extern "C" int ehm_partition_create(ehm_problem *p, int nroots, const double *ro
     const size_t WN = (size_t)W * ncand;
     A(t->alloc(&wv.node, W)); A(t->alloc(&wv.skip, W)); A(t->alloc(&wv.lb, WN)); A(t->alloc(&wv.tref, W));
     A(t->alloc(&wv.tval, WN)); A(t->alloc(&wv.titem, WN)); A(t->alloc(&wv.items, WN));
-    A(t->alloc(&wv.it_sol, WN * (n + 1))); A(t->alloc(&wv.sel, (size_t)W * kSelT)); A(t->alloc(&wv.nsel, W));
+    A(t->alloc(&wv.it_sol, WN * (n + 1))); A(t->alloc(&wv.it_pl, WN * (n + 1))); A(t->alloc(&wv.sel, (size_t)W * kSelT)); A(t->alloc(&wv.nsel, W));
     A(t->alloc(&wv.nimp, W)); A(t->alloc(&wv.conv, W)); A(t->alloc(&wv.ij, (size_t)2 * W));
     A(t->alloc(&wv.vmid, (size_t)W * n));
     const size_t PP = (size_t)W * ((kSelT + 1) * (n + 2) + 1);

@@ -75,6 +75,7 @@ struct WaveBuf {
     int *titem;         // [W][ncand]   item index of (e,c) or -1
     int2 *items;        // [W*ncand]
     double *it_sol;     // [W*ncand][n+1]
+    float *it_pl;       // [W*ncand][n+1]  tangent plane of the item's value function (ehm_solve.cuh)
     int *sel;           // [W][kSelT]
     int *nsel, *nimp, *conv, *ij;
     double *vmid;       // [W][n]
@@ -225,7 +226,8 @@ k_lcss_eval(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
         const int nd = wv.node[ec.x];
         const SolveOut o = solve_simplex<U, NX, MRI, MRC>(tb, ec.y, ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, true, ws,
-                                                    wv.it_sol + (size_t)it * (NX + 1), lane);
+                                                    wv.it_sol + (size_t)it * (NX + 1), lane,
+                                                    wv.it_pl + (size_t)it * (NX + 1));
         account(cnt, o, lane, 2, ec.y, nd);
         if (lane == 0) {
             const size_t ix = (size_t)ec.x * tb.ncand + ec.y;
@@ -234,6 +236,7 @@ k_lcss_eval(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
                 wv.lb[ix] = f32_down(o.val);
             } else {
                 wv.lb[ix] = INFINITY;  // dead on this simplex (or numerical failure)
+                wv.it_pl[(size_t)it * (NX + 1)] = -INFINITY;  // no plane
             }
         }
         __syncwarp();
@@ -369,12 +372,27 @@ k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt
 // ------------------------------------------------------------------------------------------
 // k_lcss_final: decide and act.  One warp per entry (the bound rows are copied by the warp).
 // ------------------------------------------------------------------------------------------
+// Bound of t*_c from the tangent plane P (vertex values) under vertex costs V (ehm_solve.cuh).
+template <int NX>
+__device__ __forceinline__ float plane_bound(const float (&P)[NX + 1], const double (&V)[NX + 1], double eps_a,
+                                             double k2)
+{
+    double a = INFINITY, b = INFINITY;
+#pragma unroll
+    for (int i = 0; i <= NX; ++i) {
+        a = fmin(a, (double)P[i] - V[i]);
+        b = fmin(b, (double)P[i] - k2 * V[i]);
+    }
+    return __double2float_rd(fmax(a + eps_a, b));
+}
+
 template <int NX>
 __global__ void k_lcss_final(DevTables tb, NodeStore ns, Frontier fr, WaveBuf wv, int W, Ctl *ctl)
 {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const int ncand = tb.ncand, nu = tb.nu;
+    const double k2 = 1.0 / (1.0 + tb.eps_r);
     for (int e = gw; e < W; e += nw) {
         const int nd = wv.node[e];
         if (wv.conv[e]) {  // worker.py:368-375 close leaf
@@ -440,10 +458,19 @@ __global__ void k_lcss_final(DevTables tb, NodeStore ns, Frontier fr, WaveBuf wv
                 if (lane == 0) atomicExch(&ctl->error, EHM_ECAPACITY);
                 continue;
             }
+            double Vn[NX + 1];
+            for (int i = 0; i <= NX; ++i) Vn[i] = wv.ptJ[pslot + i];
             for (int c = lane; c < ncand; c += 32) {
                 float v = wv.lb[(size_t)e * ncand + c];
                 if (c == cref) v = -INFINITY;
                 else if (v != INFINITY && v != -INFINITY && dreb > 0.0f) v = __fadd_rd(v, -dreb);
+                // this visit's tangent plane bounds t*_c under the NEW vertex costs as well
+                const int item = wv.titem[(size_t)e * ncand + c];
+                if (item >= 0 && v != INFINITY) {
+                    float P[NX + 1];
+                    for (int i = 0; i <= NX; ++i) P[i] = wv.it_pl[(size_t)item * (NX + 1) + i];
+                    if (P[0] > -INFINITY) v = fmaxf(v, plane_bound<NX>(P, Vn, tb.eps_a, k2));
+                }
                 fr.lb[(size_t)pos * ncand + c] = v;
             }
             if (lane == 0) {
@@ -474,14 +501,39 @@ __global__ void k_lcss_final(DevTables tb, NodeStore ns, Frontier fr, WaveBuf wv
             if (lane == 0) atomicExch(&ctl->error, EHM_ECAPACITY);
             continue;
         }
+        // vertex costs of the two children (side 0 replaces vertex bi, side 1 vertex bj by the midpoint)
+        const int sbi = wv.ij[2 * e], sbj = wv.ij[2 * e + 1];
+        double Vc0[NX + 1], Vc1[NX + 1];
+        for (int i = 0; i <= NX; ++i) {
+            const double base = (cstar >= 0) ? wv.ptJ[pslot + i] : Vr[i];
+            Vc0[i] = (i == sbi) ? wv.ptJ[pslot + NX + 1] : base;
+            Vc1[i] = (i == sbj) ? wv.ptJ[pslot + NX + 1] : base;
+        }
         for (int c = lane; c < ncand; c += 32) {
             float v = wv.lb[(size_t)e * ncand + c];
             if (cstar >= 0) {
                 if (c == cref) v = -INFINITY;
                 else if (v != INFINITY && v != -INFINITY && dreb > 0.0f) v = __fadd_rd(v, -dreb);
             }
-            fr.lb[(size_t)pos * ncand + c] = v;
-            fr.lb[(size_t)(pos + 1) * ncand + c] = v;
+            float v0 = v, v1 = v;
+            // the tangent plane of this visit follows the geometry (the midpoint value is the mean
+            // of the two end points) and bounds t*_c under each child's own vertex costs
+            const int item = wv.titem[(size_t)e * ncand + c];
+            if (item >= 0 && v != INFINITY) {
+                float P[NX + 1];
+                for (int i = 0; i <= NX; ++i) P[i] = wv.it_pl[(size_t)item * (NX + 1) + i];
+                if (P[0] > -INFINITY) {
+                    const float pm = __fmul_rd(0.5f, __fadd_rd(P[sbi], P[sbj])), pbi = P[sbi], pbj = P[sbj];
+                    P[sbi] = pm;
+                    v0 = fmaxf(v0, plane_bound<NX>(P, Vc0, tb.eps_a, k2));
+                    P[sbi] = pbi;
+                    P[sbj] = pm;
+                    v1 = fmaxf(v1, plane_bound<NX>(P, Vc1, tb.eps_a, k2));
+                    P[sbj] = pbj;
+                }
+            }
+            fr.lb[(size_t)pos * ncand + c] = v0;
+            fr.lb[(size_t)(pos + 1) * ncand + c] = v1;
         }
         if (lane == 0) {
             const int bi = wv.ij[2 * e], bj = wv.ij[2 * e + 1];

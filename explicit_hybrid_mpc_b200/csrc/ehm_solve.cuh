@@ -251,11 +251,18 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
 // sol (optional, global, NX+1 doubles): [beta*, V*] written for TQP / MINV.
 // Row order of the compacted tile: surviving stage rows, the NX+1 simplex rows, then (TQP)
 // the two epigraph rows -- so phase 1 simply runs on the first total-2 rows.
+// plane (optional, global, NX+1 floats, TQP): values at the vertices of R of the tangent plane
+// of the candidate's value function W_c(theta) = min_u V_c(u, theta) at the minimiser theta* of
+// the epigraph problem, lowered by a safety margin and rounded down.  W_c >= plane everywhere
+// (convexity), hence for ANY vertex costs Vr' on a sub-simplex with vertex values plane'_i
+//     t*_c >= min_i (plane'_i - Vr'_i) + eps_a   and   t*_c >= min_i (plane'_i - Vr'_i/(1+eps_r)).
+// The gradient comes from the KKT multipliers of the stage rows (oracle/ehm_oracle.c:
+// solve_simplex_qp_pl):  dW/dbeta = dV/dbeta + sum_r lam_r a_(r,beta).
 // ---------------------------------------------------------------------------------------
 template <int U, int NX, int MRI, int MRC>
 __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__restrict__ Rv,
                                   const double *__restrict__ Vr, int mode, bool phase1,
-                                  double *ws, double *sol, int lane)
+                                  double *ws, double *sol, int lane, float *plane = nullptr)
 {
     using WW = WarpWs<U, NX, MRI, MRC>;
     using W = typename WW::WS;
@@ -473,6 +480,40 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
     }
     out.status = 1;
     out.val = cs * obj + cst;
+    if (plane != nullptr && tau) {
+        const double *lv = ws + W::oL;
+        double gb[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) gb[i] = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < MRC; ++j) {
+            const int r = lane + 32 * j;
+            if (r < cnt) {
+                const double l = lv[r];
+#pragma unroll
+                for (int i = 0; i < NX; ++i) gb[i] = fma(l, Gs[(U + i) * MRP + r], gb[i]);
+            }
+        }
+        double sg = 0.0, p0 = out.val - zs[NB] * cs;
+        const double vst = p0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            double v = warp_sum(gb[i]) + fs[U + i];
+#pragma unroll
+            for (int k = 0; k < NVS; ++k) v = fma(Hs[(U + i) * NVS + k], zs[k], v);
+            gb[i] = cs * v;
+            sg += fabs(gb[i]);
+            p0 = fma(-gb[i], zs[U + i], p0);
+        }
+        const double mg = 1e-6 * (1.0 + fabs(vst) + sg);
+        if (lane == 0) plane[0] = __double2float_rd(p0 - mg);
+        if (lane >= 1 && lane <= NX) {
+            double gl = 0.0;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) gl = (lane == i + 1) ? gb[i] : gl;
+            plane[lane] = __double2float_rd(p0 + gl - mg);
+        }
+    }
     if (sol != nullptr) {
         if (lane < NX) sol[lane] = zs[U + lane];
         if (lane == NX) sol[NX] = tau ? out.val - zs[NB] * cs : out.val;

@@ -45,6 +45,13 @@ void ehmo_stats(long *out) { for (int i = 0; i < 6; ++i) out[i] = g_stat[i] + t_
  * iterate (z_k, sigma_k) is a feasible point of it; as soon as z_k leaves all (normalised)
  * slacks of the ORIGINAL rows >= TAU_INT the answer "alive" is certified (sigma* <= -TAU_INT)
  * and the remaining iterations cannot change it. */
+/* optional output of the last qp_solve of this thread: multipliers of the rows (tangent planes) */
+static __thread double *t_lam_out = NULL;
+static int g_planes = 2; /* 0 off, 1 inherited planes, 2 local planes (what the CUDA engine does) */
+static __thread double *t_planes = NULL;
+static long g_plane_skips = 0;
+long ehmo_plane_skips(void) { return g_plane_skips; }
+void ehmo_set_planes(int on) { g_planes = on; }
 static int g_early = 1;
 void ehmo_set_early_exit(int on) { g_early = on; }
 static inline double fmax2(double a, double b) { return a > b ? a : b; }
@@ -273,6 +280,7 @@ static int qp_solve_x(int nv, int m, const double *H, const double *f, const dou
         }
     }
     *obj_out = obj;
+    if (t_lam_out) memcpy(t_lam_out, lam, (size_t)m * sizeof(double));
     if (status != 0 && env_flag("EHMO_FAILTRACE", &dbg_failtrace)) {
         double rpm = 0, rdm = 0, mu = 0;
         for (int r = 0; r < m; ++r) { rpm = fmax2(rpm, fabs(rp[r])); mu += s[r] * lam[r]; }
@@ -298,11 +306,14 @@ void ehmo_set_presolve(int on) { g_presolve = on; }
  * a normalised row a'z <= h whose left-hand side cannot exceed h - TAU_DROP anywhere in that
  * box is dropped -- exact for every decision (see DESIGN.md "Row pre-solve"); it removes the
  * ~75% of the reference's big-M rows (lib/mpc_library.py:529-534) that can never bind. */
+static __thread int t_mstage = 0, t_stage_kept = 0;
 static int prep_rows(int nv, int m, const double *G, const double *h, const double *rho,
                      double *Go, double *ho, int nbox, int nsx)
 {
     int mo = 0;
+    t_stage_kept = 0;
     for (int r = 0; r < m; ++r) {
+        if (r == t_mstage) t_stage_kept = mo;
         double nrm = 0;
         for (int j = 0; j < nv; ++j) nrm = fmax2(nrm, fabs(G[r * nv + j]));
         double sc = rho[r] > 0 ? rho[r] : 1.0;
@@ -326,6 +337,7 @@ static int prep_rows(int nv, int m, const double *G, const double *h, const doub
         ho[mo] = h[r] * inv;
         ++mo;
     }
+    if (t_mstage >= m) t_stage_kept = mo;
     return mo;
 }
 
@@ -711,20 +723,56 @@ static int alive_on_simplex(ehmo_problem *pb, int c, const double *R)
 /* Solve the simplex QP of candidate c: with_tau=1 -> t*_c (eps-suboptimality epigraph
  * problem), with_tau=0 -> min_{theta in R} V*_c(theta) (lib/oracle.py:75-79).
  * returns 0 ok; zsol (nv) optional. */
+static int solve_simplex_qp_pl(ehmo_problem *pb, int c, const double *R, const double *Vr,
+                               int with_tau, double *val, double *zsol, double *plane);
 static int solve_simplex_qp(ehmo_problem *pb, int c, const double *R, const double *Vr,
                             int with_tau, double *val, double *zsol)
+{
+    return solve_simplex_qp_pl(pb, c, R, Vr, with_tau, val, zsol, NULL);
+}
+
+/* plane (n+1 values, optional, with_tau only): values at the vertices of R of the tangent plane
+ * of the candidate's value function W_c(theta) = min_u V_c(u,theta) at the minimiser theta* of
+ * the epigraph problem: W_c >= plane everywhere (convexity), so for ANY vertex costs Vr' on a
+ * sub-simplex  t*_c >= min_i (plane_i - Vr'_i) + eps_a  and  >= min_i (plane_i - Vr'_i/(1+eps_r)).
+ * Gradient from the KKT multipliers of the stage rows: dW/dbeta = dV/dbeta + sum_r lam_r a_r,beta. */
+static int solve_simplex_qp_pl(ehmo_problem *pb, int c, const double *R, const double *Vr,
+                               int with_tau, double *val, double *zsol, double *plane)
 {
     simplex_qp q;
     build_simplex_qp(pb, c, R, Vr, with_tau, &q);
     double *Gn = dalloc((size_t)q.m * q.nv), *hn = dalloc(q.m);
     double z[MAXNV], obj = 0;
+    t_mstage = pb->m;
     int mo = prep_rows(q.nv, q.m, q.G, q.h, q.rho, Gn, hn, pb->U, pb->n), st = 2;
+    const int nstage = t_stage_kept;
+    t_mstage = 0;
+    double *lam = (plane && mo > 0) ? dalloc(mo) : NULL;
     if (mo >= 0) {
         int its = 0;
+        t_lam_out = lam;
         st = qp_solve(q.nv, mo, q.H, q.f, Gn, hn, NULL, z, &obj, &its);
+        t_lam_out = NULL;
         t_stat[4]++; t_stat[5] += its;
         t_solves++;
     }
+    if (st == 0 && plane && with_tau) {
+        const int n = pb->n, U = pb->U, nv = q.nv;
+        double g[MAXNV], Vst = q.cs * obj + q.cst - q.cs * z[nv - 1], sg = 0, p0;
+        for (int i = 0; i < n; ++i) {
+            double v = q.f[U + i];
+            for (int k = 0; k < nv; ++k) v += q.H[(U + i) * nv + k] * z[k];
+            for (int r = 0; r < nstage; ++r) v += lam[r] * Gn[(size_t)r * nv + U + i];
+            g[i] = q.cs * v;
+            sg += fabs(g[i]);
+        }
+        p0 = Vst;
+        for (int i = 0; i < n; ++i) p0 -= g[i] * z[U + i];
+        const double mg = 1e-6 * (1.0 + fabs(Vst) + sg); /* safety margin of the certificate */
+        plane[0] = p0 - mg;
+        for (int i = 0; i < n; ++i) plane[i + 1] = p0 + g[i] - mg;
+    }
+    free(lam);
     if (st == 0) {
         *val = q.cs * obj + q.cst;
         if (zsol) {
@@ -774,7 +822,10 @@ int ehmo_lcss_eval(ehmo_problem *pb, const double *R, const double *Vr, int cref
     const int n = pb->n, nu = pb->nu, U = pb->U, nc = pb->ncand;
     double *ts = dalloc(nc);
     double tref = INFINITY, zref[MAXNV];
+    double *pl = (lb && g_planes) ? t_planes : NULL; /* nc x (n+1), see solve_simplex_qp_pl */
+    const double k2 = 1.0 / (1.0 + pb->eps_r);
     res->converged = 0; res->cstar = -1; res->var_small = 0; res->n_eval = 0; res->n_fail = 0;
+    res->n_plane = 0;
     /* delta_ref is feasible at every vertex by construction: no phase-1 */
     if (cref >= 0) {
         if (solve_simplex_qp(pb, cref, R, Vr, 1, &tref, zref) != 0) { tref = INFINITY; res->n_fail++; }
@@ -788,6 +839,20 @@ int ehmo_lcss_eval(ehmo_problem *pb, const double *R, const double *Vr, int cref
         if (c == cref) continue;
         if (lb && lb[c] == INFINITY) continue;                 /* dead */
         if (lb && prune && lb[c] > thr) continue;              /* cannot be improving/argmin */
+        if (pl && prune) { /* tangent-plane bound under the CURRENT vertex costs */
+            const double *P = pl + (size_t)c * (n + 1);
+            double a = INFINITY, bq = INFINITY;
+            for (int i = 0; i <= n; ++i) {
+                a = fmin(a, P[i] - Vr[i]);
+                bq = fmin(bq, P[i] - k2 * Vr[i]);
+            }
+            const double lbp = fmax2(a + pb->eps_a, bq);
+            if (lbp > thr) {
+                if (lbp > lb[c]) lb[c] = lbp;
+                res->n_plane++;
+                continue;
+            }
+        }
         int al = alive_on_simplex(pb, c, R);
         res->n_eval++;
         if (al != 1) {
@@ -796,7 +861,7 @@ int ehmo_lcss_eval(ehmo_problem *pb, const double *R, const double *Vr, int cref
             continue;
         }
         double t;
-        if (solve_simplex_qp(pb, c, R, Vr, 1, &t, NULL) != 0) {
+        if (solve_simplex_qp_pl(pb, c, R, Vr, 1, &t, NULL, pl ? pl + (size_t)c * (n + 1) : NULL) != 0) {
             res->n_fail++;
             if (lb) lb[c] = INFINITY;
             continue;
@@ -1027,7 +1092,9 @@ static void ecc_step(builder *b, long id)
         t->cand[id] = c;
         memcpy(t->vcost + id * (n + 1), Jv, sizeof(double) * (n + 1));
         memcpy(t->vinput + id * (n + 1) * nu, Uv, sizeof(double) * (n + 1) * nu);
-        double *lb = dalloc(pb->ncand);
+        /* bounds, then one tangent plane (n+1 vertex values) per candidate; -inf = none yet */
+        double *lb = dalloc((size_t)pb->ncand * (n + 2));
+        for (size_t k = pb->ncand; k < (size_t)pb->ncand * (n + 2); ++k) lb[k] = -INFINITY;
         for (int k = 0; k < pb->ncand; ++k) lb[k] = -INFINITY;
         push_task(b, id, lb);
     }
@@ -1046,8 +1113,11 @@ static void lcss_step(builder *b, long id, double *lb)
     int cref = t->cand[id];
     double th[MAXNV], Jn[MAXNV], Un[MAXNV * MAXNV];
     ehmo_lcss_result res;
+    t_planes = lb + nc;
     ehmo_lcss_eval(pb, R, Vr, cref, lb, b->prune, th, Jn, Un, &res);
+    t_planes = NULL;
     __sync_fetch_and_add(&t->nfail, res.n_fail);
+    __sync_fetch_and_add(&g_plane_skips, res.n_plane);
     if (env_flag("EHMO_TRACE", &dbg_trace))
         fprintf(stderr, "node %ld depth %d cref %d evaluated %d tref %.4g conv %d cstar %d vs %d\n",
                 id, t->depth[id], cref, res.n_eval, res.t_ref, res.converged, res.cstar, res.var_small);
@@ -1093,7 +1163,34 @@ static void lcss_step(builder *b, long id, double *lb)
         t->vcost[ch * (n + 1) + ij[side]] = Jm;
         memcpy(t->vinput + (ch * (n + 1) + ij[side]) * nu, Um, sizeof(double) * nu);
     }
-    push_task(b, l, dcopy(lb, nc));
+    /* tangent planes follow the geometry: the new vertex is the midpoint of vertices ij[0], ij[1] */
+    double *lbl = dcopy(lb, (size_t)nc * (n + 2));
+    for (int c = 0; c < nc; ++c) {
+        double *Pl = lbl + nc + (size_t)c * (n + 1), *Pr = lb + nc + (size_t)c * (n + 1);
+        const double mid = 0.5 * (Pr[ij[0]] + Pr[ij[1]]);
+        Pl[ij[0]] = mid;
+        Pr[ij[1]] = mid;
+    }
+    if (g_planes == 2) {
+        /* "local" variant (what the CUDA engine does): the planes of THIS node's evaluation
+         * tighten the children's bounds under the children's own vertex costs, then are dropped */
+        const double k2 = 1.0 / (1.0 + pb->eps_r);
+        for (int side = 0; side < 2; ++side) {
+            double *lc = side ? lb : lbl;
+            const double *Vc = t->vcost + (side ? r : l) * (n + 1);
+            for (int c = 0; c < nc; ++c) {
+                double *P = lc + nc + (size_t)c * (n + 1);
+                if (P[0] > -INFINITY && lc[c] != INFINITY) {
+                    double a = INFINITY, bq = INFINITY;
+                    for (int i = 0; i <= n; ++i) { a = fmin(a, P[i] - Vc[i]); bq = fmin(bq, P[i] - k2 * Vc[i]); }
+                    const double lbp = fmax2(a + pb->eps_a, bq);
+                    if (lbp > lc[c]) lc[c] = lbp;
+                }
+                for (int i = 0; i <= n; ++i) P[i] = -INFINITY;
+            }
+        }
+    }
+    push_task(b, l, lbl);
     push_task(b, r, lb);
 }
 

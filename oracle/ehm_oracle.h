@@ -54,6 +54,8 @@ ehmo_problem *ehmo_create(int n, int nu, int N, int K, int p,
 void ehmo_destroy(ehmo_problem *pb);
 void ehmo_set_eps(ehmo_problem *pb, double eps_a, double eps_r);
 void ehmo_set_presolve(int on); /* 1 (default): drop rows that cannot bind in the input box */
+void ehmo_set_planes(int on);     /* 1 (default): tangent-plane bounds in the partition (result-invariant) */
+long ehmo_plane_skips(void);
 void ehmo_set_early_exit(int on); /* 1 (default): stop a phase-1 LP at the first certified interior point */
 void ehmo_stats(long *out6);      /* phase-1 alive / its, phase-1 dead / its, QP solves / its */
 long ehmo_total_iters(void);
@@ -74,6 +76,7 @@ typedef struct {
     double t_ref;   /* t* of delta_ref                                              */
     int n_eval;     /* candidates whose epigraph problem was evaluated              */
     int n_fail;     /* numerical failures (should be 0)                             */
+    int n_plane;    /* candidates skipped by their tangent-plane bound              */
 } ehmo_lcss_result;
 int ehmo_lcss_eval(ehmo_problem *pb, const double *R, const double *Vr, int cand_ref,
                    double *lb, int prune, double *theta_star, double *Jv, double *Uv,

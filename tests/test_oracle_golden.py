@@ -122,3 +122,22 @@ def test_phase1_early_exit_is_exact(pendulum_roots, cpu_oracle):
     assert full['nfail'] == 0 and early['nfail'] == 0 and full['nsolves'] == early['nsolves']
     assert compare_trees(early, full, 1) <= 1e-9
     assert (i2 - i1) < 0.85 * (i1 - i0)
+
+
+def test_tangent_plane_bounds_are_result_invariant(pendulum_roots, cpu_oracle):
+    """Tangent-plane lower bounds of t*_c (DESIGN.md "Tangent-plane bounds") only skip work:
+    identical tree without them (0), with planes inherited down the lineage (1) and with the
+    per-visit planes the CUDA engine uses (2, the default); fewer sub-problems with them."""
+    from oracle.oracle_cpu import lib
+    from test_gpu_tree_parity import compare_trees
+    roots = pendulum_roots[[22, 8]]
+    out = {}
+    try:
+        for mode in (0, 1, 2):
+            lib().ehmo_set_planes(mode)
+            out[mode] = cpu_oracle.partition(roots, nthreads=4)
+            assert out[mode]['nfail'] == 0
+    finally:
+        lib().ehmo_set_planes(2)
+    assert compare_trees(out[1], out[0], 2) <= 1e-9 and compare_trees(out[2], out[0], 2) <= 1e-9
+    assert out[2]['nsolves'] < 0.95 * out[0]['nsolves'] and out[1]['nsolves'] <= out[2]['nsolves']
