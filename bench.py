@@ -332,6 +332,31 @@ def main():
                           % (len(sample), c['leaves'], c['seconds']),
                    solves_per_s=c['solves_per_s'])
 
+    # secondary: online evaluation of the produced control law, not timed above
+    online = None
+    if world == 1:
+        try:
+            from explicit_hybrid_mpc_b200.mpc_library import ExplicitMPC
+            empc = ExplicitMPC(res)
+            nq = 1 << 21
+            X = (torch.rand(nq, 4, dtype=torch.float64, device='cuda') * 2 - 1) * torch.tensor(
+                mpc.theta_scale, device='cuda')
+            empc.evaluate_batch(X[:1024])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            U_, leaf_ = empc.evaluate_batch(X)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            online = dict(kernel='k_locate', queries=nq, ms=ms, evals_per_s=nq / (ms * 1e-3),
+                          tree_nodes=int(len(empc.flat['left'])),
+                          note='ExplicitMPC.evaluate_batch on the partition of this run; the '
+                               'reference evaluates one state in 0.15-0.5 ms on a CPU '
+                               '(lib/post_process.py:331-338)')
+            empc.close()
+        except Exception as ex:   # never let the secondary metric break the headline line
+            online = dict(error=repr(ex))
+
     line = dict(
         metric=METRIC, value=value, unit='leaves/s', n_gpus=world, steps=args.steps,
         warmup=args.warmup, ms_per_step=dev_s * 1e3 / args.steps, higher_is_better=True,
@@ -354,6 +379,7 @@ def main():
         gpu_launches=int(launches_all),
         clocks=_clocks_summary(samples),
         roofline=roofline, roofline_hbm=roofline_hbm, cpu_baseline=cpu,
+        online_evaluation=online,
         rank_busy_ms_last_step=[round(x, 1) for x in busy_all.tolist()],
         wall_s_timed_region=t_total)
     print(json.dumps(line))

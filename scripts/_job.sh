@@ -1,2 +1,7 @@
-timeout 900 python -m pytest tests/test_gpu_tree_parity.py tests/test_gpu_batch_parity.py -x -q -m gpu 2>&1 | tail -5
-timeout 200 python scripts/run_partition.py 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('v11',d['device_ms'],d['nwaves'],d['nleaves'],d['nfail'],d['iters_per_solve'],d['nsolves'])"
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 400 python bench.py > gpurun_out/bench_r1_n1.json 2> gpurun_out/bench_r1_n1.err; tail -c 300 gpurun_out/bench_r1_n1.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_r1_n1.json')); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['traffic'], d['cpu_baseline'])"
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r1_reference.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/bench_r1_reference.json')); print(d['value'], d['ms_per_step'], d['cpu_baseline'])"
+python -c "
+import __graft_entry__ as g; g.smoke(); print('smoke ok')"
