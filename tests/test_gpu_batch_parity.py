@@ -97,21 +97,25 @@ def test_min_over_simplex(pendulum, pendulum_roots, cpu_oracle, gpu_oracle):
     assert int(st[0]) == 1 and _close(float(v_g[0]), v_c)
 
 
-def test_split_bit_exact(gpu_oracle, cpu_oracle):
+@pytest.mark.parametrize('n', [2, 4, 6, 8])     # cwh_z, pendulum / cwh_xy, cwh_xyz, synthetic
+def test_split_bit_exact(n, gpu_oracle, cpu_oracle):
     import torch
     from explicit_hybrid_mpc_b200 import _capi
     rng = np.random.default_rng(7)
-    B, n = 512, 4
+    B = 512
     R = rng.standard_normal((B, n + 1, n))
     # force ties: regular-ish simplices with repeated edge lengths
     R[:64] = np.round(R[:64] * 2) / 2
     Rt = torch.as_tensor(R).cuda()
-    S1, S2 = torch.empty_like(Rt), torch.empty_like(Rt)
-    ij = torch.empty(B, 2, dtype=torch.int32, device='cuda')
-    _capi.check(_capi.lib().ehm_split_batch(n, B, Rt.data_ptr(), S1.data_ptr(), S2.data_ptr(),
-                                            ij.data_ptr(), None))
-    S1, S2, ij = S1.cpu().numpy(), S2.cpu().numpy(), ij.cpu().numpy()
+    S1t, S2t = torch.empty_like(Rt), torch.empty_like(Rt)
+    ijt = torch.empty(B, 2, dtype=torch.int32, device='cuda')
+    _capi.check(_capi.lib().ehm_split_batch(n, B, Rt.data_ptr(), S1t.data_ptr(), S2t.data_ptr(),
+                                            ijt.data_ptr(), None))
+    S1, S2, ij = S1t.cpu().numpy(), S2t.cpu().numpy(), ijt.cpu().numpy()
     for b in range(B):
         a1, a2, aij = cpu_oracle.split_along_longest_edge(R[b])
         assert tuple(ij[b]) == tuple(aij)
         assert np.array_equal(S1[b], a1) and np.array_equal(S2[b], a2)   # bit exact
+    # empty batch: a no-op, not an error
+    _capi.check(_capi.lib().ehm_split_batch(n, 0, Rt.data_ptr(), S1t.data_ptr(), S2t.data_ptr(),
+                                            ijt.data_ptr(), None))
