@@ -115,9 +115,10 @@ k_simplex_batch(DevTables tb, int B, const double *__restrict__ R, const double 
     }
 }
 
-// Longest-edge bisection, one thread per simplex (lib/tools.py:224-257).  The squared edge
-// length is accumulated left to right with explicit round-to-nearest mul/add (no FMA) so
-// that the first-maximum decision is bit-identical to the CPU restatement.
+// Longest-edge bisection, one thread per simplex (lib/tools.py:224-257).  Edge length =
+// sqrt of a left-to-right chain of fused multiply-adds: the arithmetic of the reference's
+// la.norm(R[i]-R[j]) (numpy: sqrt(x.dot(x)), BLAS dot of a short vector), so that ties between
+// edges of equal length break exactly as in the reference; first maximum wins.
 __global__ void k_split_batch(int n, int B, const double *__restrict__ R, double *S1, double *S2,
                               int *ij)
 {
@@ -131,10 +132,11 @@ __global__ void k_split_batch(int n, int B, const double *__restrict__ R, double
             double acc = 0.0;
             for (int k = 0; k < n; ++k) {
                 const double d = __dsub_rn(Rb[i * n + k], Rb[j * n + k]);
-                acc = __dadd_rn(acc, __dmul_rn(d, d));
+                acc = __fma_rn(d, d, acc);
             }
-            if (acc > best) {
-                best = acc;
+            const double len = __dsqrt_rn(acc);
+            if (len > best) {
+                best = len;
                 bi = i;
                 bj = j;
             }

@@ -118,10 +118,11 @@ __device__ void longest_edge(const double *R, int &bi, int &bj)
             double acc = 0.0;
             for (int k = 0; k < NX; ++k) {
                 const double d = __dsub_rn(R[i * NX + k], R[j * NX + k]);
-                acc = __dadd_rn(acc, __dmul_rn(d, d));
+                acc = __fma_rn(d, d, acc);   // the reference's la.norm arithmetic, see k_split_batch
             }
-            if (acc > best) {
-                best = acc;
+            const double len = __dsqrt_rn(acc);
+            if (len > best) {
+                best = len;
                 bi = i;
                 bj = j;
             }

@@ -7,6 +7,7 @@ import itertools
 import math
 
 import numpy as np
+import numpy.linalg as la
 
 from .tree import NodeData, Tree
 
@@ -19,19 +20,13 @@ def simplex_volume(R):
 
 
 def split_along_longest_edge(R):
-    """``lib/tools.py:224-257``.  The longest edge is the first maximum, in
-    ``itertools.combinations`` order, of the squared Euclidean length accumulated left to
-    right in fp64 (the rule the CUDA engine implements with non-fused mul/add)."""
+    """``lib/tools.py:224-257``: the longest edge is the first maximum, in
+    ``itertools.combinations`` order, of ``la.norm(R[i]-R[j])`` -- the reference's own formula
+    (NumPy evaluates it as the square root of a left-to-right fused-multiply-add chain, which is
+    what the CUDA kernels and the CPU oracle restate bit for bit)."""
     R = np.asarray(R, dtype=float)
     combos = list(itertools.combinations(range(R.shape[0]), 2))
-    best, idx = -1.0, 0
-    for q, (i, j) in enumerate(combos):
-        acc = 0.0
-        for k in range(R.shape[1]):
-            d = R[i, k] - R[j, k]
-            acc = acc + d * d
-        if acc > best:
-            best, idx = acc, q
+    idx = int(np.argmax([la.norm(R[i] - R[j]) for i, j in combos]))
     i, j = combos[idx]
     v_mid = (R[i] + R[j]) / 2.
     S_1, S_2 = R.copy(), R.copy()

@@ -962,17 +962,23 @@ int ehmo_bar_d(ehmo_problem *pb, const double *R, const double *Vr, int cref,
  * that CPU and GPU take bit-identical decisions (DESIGN.md "bit-exact geometry"). */
 void ehmo_split(int n, const double *R, double *S1, double *S2, int *ij)
 {
+    /* lib/tools.py:245-250: argmax (first maximum) over itertools.combinations of
+     * la.norm(R[i]-R[j]).  numpy's norm of a 1-D vector is sqrt(x.dot(x)); for these short
+     * vectors the BLAS dot is a left-to-right chain of fused multiply-adds starting from 0
+     * (verified against numpy 2.3 / OpenBLAS 0.3.30 on 20000 vectors, tests/test_oracle_golden.py),
+     * so that is the arithmetic restated here -- ties between edges of equal length are
+     * decided by exactly these roundings. */
     int bi = 0, bj = 1;
     double best = -1.0;
     for (int i = 0; i <= n; ++i)
         for (int j = i + 1; j <= n; ++j) {
-            volatile double acc = 0.0;
+            double acc = 0.0;
             for (int k = 0; k < n; ++k) {
                 volatile double d = R[i * n + k] - R[j * n + k];
-                volatile double d2 = d * d;
-                acc = acc + d2;
+                acc = fma(d, d, acc);
             }
-            if (acc > best) { best = acc; bi = i; bj = j; }
+            const double len = sqrt(acc);
+            if (len > best) { best = len; bi = i; bj = j; }
         }
     memcpy(S1, R, sizeof(double) * (n + 1) * n);
     memcpy(S2, R, sizeof(double) * (n + 1) * n);

@@ -73,6 +73,21 @@ def test_tree_equals_cpu_oracle(sel, pendulum_roots, cpu_oracle, gpu_oracle):
     print('nodes %d leaves %d worst rel cost diff %.2e' % (res.nnodes, res.stats['nleaves'], worst))
 
 
+def test_tree_equals_reference_worker_recursion(pendulum_roots, gpu_oracle):
+    """The device loop against the tree built by the REFERENCE'S OWN Worker.ecc / Worker.lcss /
+    split code over the six-method oracle API (tests/golden/make_worker_golden.py): topology,
+    vertices (bit-exact), commutations identical; costs within 1e-6 relative."""
+    import os
+    from conftest import GOLDEN
+    from explicit_hybrid_mpc_b200.partition import partition
+    from test_oracle_golden import check_against_worker_golden
+    z = np.load(os.path.join(GOLDEN, 'worker_tree_golden.npz'))
+    roots = pendulum_roots[z['root_ids']]
+    res = partition(gpu_oracle, roots, wave=128)
+    assert res.stats['nfail'] == 0
+    check_against_worker_golden(_gpu_arrays(res), z, len(roots), cost_rtol=1e-6, input_atol=2e-3)
+
+
 @pytest.mark.parametrize('base', [22, 0])
 def test_deep_config_tree_equals_cpu_oracle(base, pendulum, pendulum_roots):
     """BASELINE config 3 (abs_frac 0.03 / eps_r 0.05, the reference's pairing table

@@ -69,20 +69,64 @@ def test_problem_lowering_matches_appendix_a(pendulum):
 
 
 def test_split_matches_reference_rule(cpu_oracle):
-    """tools.split_along_longest_edge: first maximum in itertools.combinations order."""
+    """tools.split_along_longest_edge (lib/tools.py:245-250): first maximum, in
+    itertools.combinations order, of la.norm(R[i]-R[j]) -- evaluated here with NumPy exactly as
+    the reference writes it, against the oracle's restatement (sqrt of an FMA chain)."""
     import itertools
+    import numpy.linalg as la
+    from explicit_hybrid_mpc_b200 import tools
     rng = np.random.default_rng(3)
-    for _ in range(200):
-        R = np.round(rng.standard_normal((5, 4)) * 4) / 4     # many exact ties
+    for trial in range(600):
+        n = (2, 4, 6, 8)[trial % 4]
+        if trial % 3 == 0:
+            R = np.round(rng.standard_normal((n + 1, n)) * 4) / 4     # many exact ties
+        elif trial % 3 == 1:
+            # repeated bisection of a regular-ish simplex: edges equal up to rounding noise
+            R = rng.standard_normal((n + 1, n)) * np.array([1.0, 0.087, 1.0, 0.35, 1, 1, 1, 1][:n])
+            for _ in range(trial % 7):
+                R = cpu_oracle.split_along_longest_edge(R)[trial % 2]
+        else:
+            R = rng.standard_normal((n + 1, n))
         S1, S2, ij = cpu_oracle.split_along_longest_edge(R)
-        combos = list(itertools.combinations(range(5), 2))
-        k = int(np.argmax([np.linalg.norm(R[a] - R[b]) ** 2 for a, b in combos]))
-        # np.linalg.norm may differ in the last bit; the oracle's rule is the exact-sum one
-        d2 = [sum((R[a, q] - R[b, q]) ** 2 for q in range(4)) for a, b in combos]
-        assert ij == combos[int(np.argmax(d2))]
-        assert d2[k] == max(d2)
-        mid = (R[ij[0]] + R[ij[1]]) / 2
+        combos = list(itertools.combinations(range(n + 1), 2))
+        k = int(np.argmax([la.norm(R[a] - R[b]) for a, b in combos]))     # the reference's line
+        assert ij == combos[k]
+        mid = (R[ij[0]] + R[ij[1]]) / 2.
         assert np.array_equal(S1[ij[0]], mid) and np.array_equal(S2[ij[1]], mid)
+        m1, m2, mij = tools.split_along_longest_edge(R)                   # host mirror
+        assert mij == ij and np.array_equal(m1, S1) and np.array_equal(m2, S2)
+
+
+def test_worker_recursion_golden(pendulum, pendulum_roots, cpu_oracle):
+    """The fused ECC/L-CSS loop of the oracle reproduces, node for node, the tree that the
+    REFERENCE'S OWN Worker.ecc / Worker.lcss / tools.split_along_longest_edge code
+    (lib/worker.py:241-417, imported from /root/reference) built over the six-method oracle API
+    (tests/golden/make_worker_golden.py)."""
+    from test_gpu_tree_parity import _by_path
+    z = np.load(os.path.join(GOLDEN, 'worker_tree_golden.npz'))
+    roots = pendulum_roots[z['root_ids']]
+    r = cpu_oracle.partition(roots, nthreads=4)
+    assert r['error'] == 0 and r['nfail'] == 0
+    check_against_worker_golden(r, z, len(roots))
+
+
+def check_against_worker_golden(r, z, nroots, cost_rtol=0.0, input_atol=0.0):
+    """r: flat node arrays of a partition of the golden's root simplices; z: the golden npz."""
+    from test_gpu_tree_parity import _by_path
+    pc = _by_path(r, nroots)
+    gp = {str(p): i for i, p in enumerate(z['paths'])}
+    assert set(pc) == set(gp), 'topology differs: %d vs %d nodes' % (len(pc), len(gp))
+    for p, i in gp.items():
+        j = pc[p]
+        assert np.array_equal(z['vertices'][i], r['vertices'][j]), p          # bit exact
+        assert bool(z['leaf'][i]) == (r['left'][j] < 0), p
+        assert int(z['cand'][i]) == int(r['cand'][j]), p
+        if z['leaf'][i]:
+            assert bool(z['closed'][i]) and int(r['closed'][j]) == 1, p
+        if z['cand'][i] >= 0:
+            tol = cost_rtol * np.maximum(1.0, np.abs(z['vcost'][i]))
+            assert (np.abs(z['vcost'][i] - r['vcost'][j]) <= tol).all(), p
+            assert np.abs(z['vinput'][i] - r['vinput'][j]).max() <= input_atol, p
 
 
 def test_row_presolve_is_exact(pendulum, pendulum_roots, cpu_oracle):
