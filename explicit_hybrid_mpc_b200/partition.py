@@ -68,6 +68,46 @@ class PartitionResult:
                 stack.append((t.right, self.right[i]))
         return root
 
+    def overall_status(self, total_volume=None):
+        """The ``overall`` block of the reference's status / statistics files
+        (``lib/scheduler.py:293-305``) computed from the node store and the device counters:
+        volume filled (closed leaves), simplex count, queue length, time elapsed."""
+        from .tools import simplex_volume
+        leaves = self.leaf_ids()
+        closed = leaves[self.closed[leaves] == 1]
+        vol = float(sum(simplex_volume(self.vertices[i]) for i in closed))
+        if total_volume is None:
+            total_volume = float(sum(simplex_volume(self.vertices[i]) for i in np.nonzero(self.depth == 0)[0]))
+        st = self.stats
+        return dict(num_proc_active=0, num_proc_failed=0,
+                    num_tasks_in_queue=int(st.get('open_left', 0)),
+                    volume_filled_total=vol,
+                    volume_filled_frac=vol / total_volume if total_volume else 0.0,
+                    simplex_count_total=int(len(closed)),
+                    time_elapsed=float(st.get('wall_s', st.get('device_ms', 0.0) * 1e-3)),
+                    algorithms_running=[], time_active_total=float(st.get('device_ms', 0.0)) * 1e-3,
+                    time_idle_total=0.0, eta=0 if not st.get('open_left', 0) else None,
+                    max_depth=int(self.depth.max()), oracle_solves=int(st.get('nsolves', 0)),
+                    oracle_failures=int(st.get('nfail', 0)))
+
+    def write_status(self, path, total_volume=None):
+        """``status.txt`` in the reference's layout (``lib/scheduler.py:311-333``, overall part)."""
+        o = self.overall_status(total_volume)
+        with open(path, 'w') as f:
+            f.write('\n'.join([
+                '# overall',
+                'number of processes active: %d' % o['num_proc_active'],
+                'number of processes failed: %d' % o['num_proc_failed'],
+                'number of tasks queue: %d' % o['num_tasks_in_queue'],
+                'volume filled (total [%%]): %.4e' % (o['volume_filled_frac'] * 100.),
+                'simplex_count: %d' % o['simplex_count_total'],
+                'time elapsed [s]: %d' % o['time_elapsed'],
+                'time active (total for all processes [s]): %.0f' % o['time_active_total'],
+                'time idle (total for all processes [s]): %.0f' % o['time_idle_total'],
+                'ETA [s]: %s' % str(o['eta']),
+            ]) + '\n\n')
+        return o
+
     def graft(self, initial_tree):
         """Graft the partitioned subtrees onto the leaves of the initial triangulation tree
         (what ``build_tree`` does with the ``branch_<location>.pkl`` files,

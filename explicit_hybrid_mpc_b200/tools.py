@@ -35,6 +35,27 @@ def split_along_longest_edge(R):
     return S_1, S_2, (i, j)
 
 
+def kuhn_triangulation(lower, upper, limit=None):
+    """Deterministic triangulation of the box [lower, upper] into n! simplices (Kuhn / Freudenthal):
+    one simplex per permutation p of the axes, vertices v_0 = lower, v_k = v_(k-1) + e_p(k) * width.
+    Unlike ``delaunay`` (Qhull) the result does not depend on library versions or vertex order
+    (SURVEY 8f row 3).  Permutations in ``itertools.permutations`` order; ``limit`` keeps the first
+    ``limit`` of them (BASELINE config 5: 1024 of 8! = 40320)."""
+    lower, upper = np.asarray(lower, dtype=float), np.asarray(upper, dtype=float)
+    n = lower.shape[0]
+    out = []
+    for q, perm in enumerate(itertools.permutations(range(n))):
+        if limit is not None and q >= limit:
+            break
+        v = lower.copy()
+        S = [v.copy()]
+        for ax in perm:
+            v[ax] = upper[ax]
+            S.append(v.copy())
+        out.append(np.array(S))
+    return np.array(out)
+
+
 def delaunay(R):
     """``lib/tools.py:152-189``: Delaunay triangulation of the polytope with vertex rows R
     into a right-spine binary tree whose leaves are the simplices."""

@@ -12,7 +12,9 @@ restatement of it.  Only the MPI task hand-over (``offload_child_computation``) 
 to "do it yourself", which the reference itself does whenever no worker is idle
 (``lib/worker.py:230-239``).  Needs /root/reference; run here only (about two minutes):
 
-    python tests/golden/make_worker_golden.py
+    python tests/golden/make_worker_golden.py                 # roots 22, 44 -> worker_tree_golden.npz
+    python tests/golden/make_worker_golden.py 0 root0         # root 0 (contains a swap-in-place
+                                                              # visit) -> worker_tree_golden_root0.npz
 """
 import os
 import sys
@@ -30,6 +32,11 @@ EPS_A, EPS_R = 19.21220798973866, 1.0
 
 
 def main():
+    global ROOT_IDS
+    suffix = ''
+    if len(sys.argv) > 1:
+        ROOT_IDS = [int(x) for x in sys.argv[1].split(',')]
+        suffix = '_' + sys.argv[2]
     from explicit_hybrid_mpc_b200.mpc_library import InvertedPendulumOnCart
     from oracle.oracle_cpu import CpuOracle
     mpc = InvertedPendulumOnCart()
@@ -71,7 +78,7 @@ def main():
             if not t.is_leaf():
                 stack.append((t.left, p + '0'))
                 stack.append((t.right, p + '1'))
-    np.savez_compressed(os.path.join(HERE, 'worker_tree_golden.npz'), root_ids=np.array(ROOT_IDS),
+    np.savez_compressed(os.path.join(HERE, 'worker_tree_golden%s.npz' % suffix), root_ids=np.array(ROOT_IDS),
                         eps=np.array([EPS_A, EPS_R]), paths=np.array(out['paths']),
                         vertices=np.array(out['vertices']), cand=np.array(out['cand']),
                         vcost=np.array(out['vcost']), vinput=np.array(out['vinput']),

@@ -176,3 +176,36 @@ def test_partition_distributed_gloo_world2(kw):
     ch = np.concatenate([out['left'][inner], out['right'][inner]])
     assert len(set(ch.tolist())) == len(ch) == len(out['left']) - 7
     assert rounds >= 1                                        # the rebalance path was exercised
+
+
+def test_kuhn_triangulation_tiles_the_box():
+    import math
+    from explicit_hybrid_mpc_b200.tools import kuhn_triangulation, simplex_volume
+    lo, hi = np.array([-1.0, -0.087, -1.0, -0.35]), np.array([1.0, 0.087, 1.0, 0.35])
+    T = kuhn_triangulation(lo, hi)
+    assert T.shape == (math.factorial(4), 5, 4)
+    assert abs(sum(simplex_volume(S) for S in T) - np.prod(hi - lo)) <= 1e-12 * np.prod(hi - lo)
+    # random points fall in exactly one simplex (up to boundaries)
+    rng = np.random.default_rng(0)
+    for x in lo + rng.random((200, 4)) * (hi - lo):
+        inside = 0
+        for S in T:
+            al = np.linalg.solve(np.column_stack([v - S[0] for v in S[1:]]), x - S[0])
+            inside += (al.min() >= -1e-12) and (al.sum() <= 1 + 1e-12)
+        assert inside == 1
+    assert kuhn_triangulation(-np.ones(8), np.ones(8), limit=1024).shape == (1024, 9, 8)
+
+
+def test_overall_status_fields(tmp_path):
+    """status.txt / statistics 'overall' block (lib/scheduler.py:293-333) from a node store."""
+    from explicit_hybrid_mpc_b200.partition import PartitionResult
+    eng = FakeEngine(None, np.array([[[0.0], [1.0]], [[1.0], [3.0]]]))
+    eng.advance(0)
+    arr = eng.fetch()
+    res = PartitionResult(arr, dict(nleaves=int((arr['closed'] == 1).sum()), open_left=0, device_ms=12.0,
+                                    nsolves=5, nfail=0), None)
+    o = res.write_status(str(tmp_path / 'status.txt'))
+    assert abs(o['volume_filled_total'] - 3.0) < 1e-12 and abs(o['volume_filled_frac'] - 1.0) < 1e-12
+    assert o['simplex_count_total'] == int((arr['closed'] == 1).sum()) and o['num_tasks_in_queue'] == 0
+    txt = open(str(tmp_path / 'status.txt')).read()
+    assert 'volume filled (total [%]): 1.0000e+02' in txt and 'simplex_count: %d' % o['simplex_count_total'] in txt
