@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 from conftest import GOLDEN
 
@@ -97,13 +98,14 @@ def test_split_matches_reference_rule(cpu_oracle):
         assert mij == ij and np.array_equal(m1, S1) and np.array_equal(m2, S2)
 
 
-def test_worker_recursion_golden(pendulum, pendulum_roots, cpu_oracle):
+@pytest.mark.parametrize('fixture', ['worker_tree_golden.npz', 'worker_tree_golden_root0.npz'])
+def test_worker_recursion_golden(fixture, pendulum, pendulum_roots, cpu_oracle):
     """The fused ECC/L-CSS loop of the oracle reproduces, node for node, the tree that the
     REFERENCE'S OWN Worker.ecc / Worker.lcss / tools.split_along_longest_edge code
     (lib/worker.py:241-417, imported from /root/reference) built over the six-method oracle API
-    (tests/golden/make_worker_golden.py)."""
-    from test_gpu_tree_parity import _by_path
-    z = np.load(os.path.join(GOLDEN, 'worker_tree_golden.npz'))
+    (tests/golden/make_worker_golden.py).  The root-0 fixture (2035 nodes) contains a swap-in-place
+    visit (lib/worker.py:396-401)."""
+    z = np.load(os.path.join(GOLDEN, fixture))
     roots = pendulum_roots[z['root_ids']]
     r = cpu_oracle.partition(roots, nthreads=4)
     assert r['error'] == 0 and r['nfail'] == 0
