@@ -15,6 +15,9 @@ to "do it yourself", which the reference itself does whenever no worker is idle
     python tests/golden/make_worker_golden.py                 # roots 22, 44 -> worker_tree_golden.npz
     python tests/golden/make_worker_golden.py 0 root0         # root 0 (contains a swap-in-place
                                                               # visit) -> worker_tree_golden_root0.npz
+    python tests/golden/make_worker_golden.py 22 deep deep    # BASELINE config 3 (abs_frac 0.03 /
+                                                              # eps_r 0.05) on a depth-5 descendant of
+                                                              # root 22 -> worker_tree_golden_deep.npz
 """
 import os
 import sys
@@ -32,11 +35,14 @@ EPS_A, EPS_R = 19.21220798973866, 1.0
 
 
 def main():
-    global ROOT_IDS
+    global ROOT_IDS, EPS_A, EPS_R
     suffix = ''
+    deep = len(sys.argv) > 3 and sys.argv[3] == 'deep'
     if len(sys.argv) > 1:
         ROOT_IDS = [int(x) for x in sys.argv[1].split(',')]
         suffix = '_' + sys.argv[2]
+    if deep:
+        EPS_A, EPS_R = 19.21220798973866 / 0.25 * 0.03, 0.05
     from explicit_hybrid_mpc_b200.mpc_library import InvertedPendulumOnCart
     from oracle.oracle_cpu import CpuOracle
     mpc = InvertedPendulumOnCart()
@@ -59,6 +65,13 @@ def main():
         w.alg_call(which_alg, child, location))
     sys.setrecursionlimit(10000)
     roots = np.load(os.path.join(HERE, 'pendulum_roots.npy'))[ROOT_IDS]
+    if deep:   # a depth-5 descendant, cut with the reference's own split
+        sub = []
+        for R in roots:
+            for d in range(5):
+                R = ref_tools.split_along_longest_edge(R)[d % 2]
+            sub.append(R)
+        roots = np.array(sub)
     out = dict(paths=[], vertices=[], cand=[], vcost=[], vinput=[], leaf=[], closed=[])
     for r, R in enumerate(roots):
         top = ref_tree.Tree(ref_tree.NodeData(vertices=R.copy()))
@@ -79,6 +92,7 @@ def main():
                 stack.append((t.left, p + '0'))
                 stack.append((t.right, p + '1'))
     np.savez_compressed(os.path.join(HERE, 'worker_tree_golden%s.npz' % suffix), root_ids=np.array(ROOT_IDS),
+                        roots=roots,
                         eps=np.array([EPS_A, EPS_R]), paths=np.array(out['paths']),
                         vertices=np.array(out['vertices']), cand=np.array(out['cand']),
                         vcost=np.array(out['vcost']), vinput=np.array(out['vinput']),

@@ -73,18 +73,17 @@ def test_tree_equals_cpu_oracle(sel, pendulum_roots, cpu_oracle, gpu_oracle):
     print('nodes %d leaves %d worst rel cost diff %.2e' % (res.nnodes, res.stats['nleaves'], worst))
 
 
-@pytest.mark.parametrize('fixture', ['worker_tree_golden.npz', 'worker_tree_golden_root0.npz'])
-def test_tree_equals_reference_worker_recursion(fixture, pendulum_roots, gpu_oracle):
-    """The device loop against the tree built by the REFERENCE'S OWN Worker.ecc / Worker.lcss /
+@pytest.mark.parametrize('fixture', ['worker_tree_golden.npz', 'worker_tree_golden_root0.npz',
+                                     'worker_tree_golden_deep.npz'])
+def test_tree_equals_reference_worker_recursion(fixture, pendulum, pendulum_roots):
+    """The device loop against the trees built by the REFERENCE'S OWN Worker.ecc / Worker.lcss /
     split code over the six-method oracle API (tests/golden/make_worker_golden.py): topology,
     vertices (bit-exact), commutations identical; costs within 1e-6 relative."""
-    import os
-    from conftest import GOLDEN
+    from explicit_hybrid_mpc_b200.oracle import Oracle
     from explicit_hybrid_mpc_b200.partition import partition
-    from test_oracle_golden import check_against_worker_golden
-    z = np.load(os.path.join(GOLDEN, fixture))
-    roots = pendulum_roots[z['root_ids']]
-    res = partition(gpu_oracle, roots, wave=128)
+    from test_oracle_golden import check_against_worker_golden, worker_fixture
+    z, roots, eps_a, eps_r = worker_fixture(fixture, pendulum_roots)
+    res = partition(Oracle(pendulum, eps_a, eps_r), roots, wave=128)
     assert res.stats['nfail'] == 0
     check_against_worker_golden(_gpu_arrays(res), z, len(roots), cost_rtol=1e-6, input_atol=2e-3)
 

@@ -98,16 +98,28 @@ def test_split_matches_reference_rule(cpu_oracle):
         assert mij == ij and np.array_equal(m1, S1) and np.array_equal(m2, S2)
 
 
-@pytest.mark.parametrize('fixture', ['worker_tree_golden.npz', 'worker_tree_golden_root0.npz'])
-def test_worker_recursion_golden(fixture, pendulum, pendulum_roots, cpu_oracle):
+WORKER_FIXTURES = ['worker_tree_golden.npz', 'worker_tree_golden_root0.npz', 'worker_tree_golden_deep.npz']
+
+
+def worker_fixture(name, pendulum_roots):
+    """(golden npz, root simplices, eps_a, eps_r) of a make_worker_golden.py fixture"""
+    z = np.load(os.path.join(GOLDEN, name))
+    roots = z['roots'] if 'roots' in z.files else pendulum_roots[z['root_ids']]
+    return z, roots, float(z['eps'][0]), float(z['eps'][1])
+
+
+@pytest.mark.parametrize('fixture', WORKER_FIXTURES)
+def test_worker_recursion_golden(fixture, pendulum, pendulum_roots):
     """The fused ECC/L-CSS loop of the oracle reproduces, node for node, the tree that the
     REFERENCE'S OWN Worker.ecc / Worker.lcss / tools.split_along_longest_edge code
     (lib/worker.py:241-417, imported from /root/reference) built over the six-method oracle API
     (tests/golden/make_worker_golden.py).  The root-0 fixture (2035 nodes) contains a swap-in-place
-    visit (lib/worker.py:396-401)."""
-    z = np.load(os.path.join(GOLDEN, fixture))
-    roots = pendulum_roots[z['root_ids']]
-    r = cpu_oracle.partition(roots, nthreads=4)
+    visit (lib/worker.py:396-401); the deep fixture is BASELINE config 3 (abs_frac 0.03 /
+    eps_r 0.05) on a depth-5 descendant of root 22."""
+    from oracle.oracle_cpu import CpuOracle
+    z, roots, eps_a, eps_r = worker_fixture(fixture, pendulum_roots)
+    cpu = CpuOracle(pendulum.problem, eps_a, eps_r, pendulum.theta_scale)
+    r = cpu.partition(roots, nthreads=4)
     assert r['error'] == 0 and r['nfail'] == 0
     check_against_worker_golden(r, z, len(roots))
 
