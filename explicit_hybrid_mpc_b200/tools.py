@@ -16,7 +16,7 @@ def simplex_volume(R):
     """``lib/tools.py:134-150``: |det[v1-v0 ... vn-v0]| / n!"""
     R = np.asarray(R, dtype=float)
     M = np.column_stack([v - R[0] for v in R[1:]])
-    return abs(np.linalg.det(M)) / math.factorial(R.shape[0] - 1)
+    return np.abs(1. / math.factorial(R.shape[0] - 1) * la.det(M))   # the reference's expression, bit for bit
 
 
 def split_along_longest_edge(R):

@@ -199,3 +199,23 @@ def test_tangent_plane_bounds_are_result_invariant(pendulum_roots, cpu_oracle):
         lib().ehmo_set_planes(2)
     assert compare_trees(out[1], out[0], 2) <= 1e-9 and compare_trees(out[2], out[0], 2) <= 1e-9
     assert out[2]['nsolves'] < 0.95 * out[0]['nsolves'] and out[1]['nsolves'] <= out[2]['nsolves']
+
+
+def test_geometry_helpers_match_reference_outputs(pendulum_roots, cpu_oracle):
+    """tools.delaunay / join_triangulation / simplex_volume / split_along_longest_edge: the host
+    mirror, the CPU oracle and the roots fixture against outputs of the reference's own
+    lib/tools.py functions (tests/golden/make_tools_golden.py)."""
+    from explicit_hybrid_mpc_b200 import tools
+    from explicit_hybrid_mpc_b200.partition import roots_of
+    z = np.load(os.path.join(GOLDEN, 'tools_golden.npz'))
+    assert np.array_equal(z['roots'], pendulum_roots)
+    trees = [tools.delaunay(s)[0] for s in z['slabs']]                  # examples.py:155-160
+    tools.join_triangulation(trees[1], trees[2])
+    tools.join_triangulation(trees[0], trees[1])
+    assert np.array_equal(np.array(roots_of(trees[0])), z['roots'])
+    for R, vol, S1, S2, ij in zip(z['simplices'], z['volumes'], z['S1'], z['S2'], z['ij']):
+        assert tools.simplex_volume(R) == vol                               # bit exact
+        assert abs(cpu_oracle.simplex_volume(R) - vol) <= 1e-12 * abs(vol)
+        for impl in (tools.split_along_longest_edge, cpu_oracle.split_along_longest_edge):
+            a, b, c = impl(R)
+            assert tuple(c) == tuple(ij) and np.array_equal(a, S1) and np.array_equal(b, S2)
