@@ -5,7 +5,8 @@ Generate ``tests/golden/tools_golden.npz`` with the REFERENCE'S OWN geometry hel
 initial triangulation exactly as ``examples.pendulum_example`` (:120-163) assembles it -- three
 velocity slabs, each Delaunay-triangulated, joined -- on itertools.product-ordered box vertices
 (cdd, which orders them in the reference, is not installable), plus volumes and splits of random
-simplices.  ``tests/golden/pendulum_roots.npy`` is the leaf list of that tree.  Run here only:
+simplices, and the eps_a that ``examples.create_oracle`` (:18-47) derives from abs_frac.
+``tests/golden/pendulum_roots.npy`` is the leaf list of that tree.  Run here only:
 
     python tests/golden/make_tools_golden.py
 """
@@ -23,8 +24,17 @@ import make_golden  # noqa: E402
 
 
 def main():
+    # this repository's packages first (the reference has modules named oracle / tools / tree too)
+    from explicit_hybrid_mpc_b200.mpc_library import InvertedPendulumOnCart
+    from oracle.oracle_cpu import CpuOracle
+    mine = InvertedPendulumOnCart()
+    for name in [k for k in sys.modules if k == 'oracle' or k.startswith('oracle.')]:
+        sys.modules.pop(name)
     ref_p = make_golden.import_reference_pendulum()
+    import examples as ref_examples
     import tools as ref_tools
+    # examples.create_oracle (:18-47) with its Oracle class answered by the CPU oracle: eps_a
+    ref_examples.Oracle = lambda mpc, eps_a, eps_r: CpuOracle(mine.problem, eps_a, eps_r, mine.theta_scale)
 
     def box(lo_hi):
         return np.array(list(itertools.product(*lo_hi)))
@@ -45,6 +55,10 @@ def main():
             stack.append(t.left)
     leaves = np.array(leaves)
     assert np.array_equal(leaves, np.load(os.path.join(HERE, 'pendulum_roots.npy')))
+    full = box([(-pe, pe), (-ae, ae), (-ve, ve), (-re_, re_)])
+    orc = ref_examples.create_oracle(ref_p, full, 0.25, None, 1.0)         # BASELINE config 2
+    eps_a_025 = orc.eps_a
+    eps_a_003 = ref_examples.create_oracle(ref_p, full, 0.03, None, 0.05).eps_a   # config 3
     rng = np.random.default_rng(11)
     simplices, vols, s1, s2, ij = [], [], [], [], []
     for k in range(200):
@@ -55,7 +69,7 @@ def main():
         simplices.append(R); vols.append(ref_tools.simplex_volume(R)); s1.append(a); s2.append(b); ij.append(c)
     np.savez_compressed(os.path.join(HERE, 'tools_golden.npz'), slabs=np.array(slabs), roots=leaves,
                         simplices=np.array(simplices), volumes=np.array(vols), S1=np.array(s1),
-                        S2=np.array(s2), ij=np.array(ij))
+                        S2=np.array(s2), ij=np.array(ij), eps_a=np.array([eps_a_025, eps_a_003]))
     print('saved', len(leaves), 'roots,', len(simplices), 'simplices')
 
 

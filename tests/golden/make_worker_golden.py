@@ -15,9 +15,13 @@ to "do it yourself", which the reference itself does whenever no worker is idle
     python tests/golden/make_worker_golden.py                 # roots 22, 44 -> worker_tree_golden.npz
     python tests/golden/make_worker_golden.py 0 root0         # root 0 (contains a swap-in-place
                                                               # visit) -> worker_tree_golden_root0.npz
-    python tests/golden/make_worker_golden.py 22 deep deep    # BASELINE config 3 (abs_frac 0.03 /
-                                                              # eps_r 0.05) on a depth-5 descendant of
-                                                              # root 22 -> worker_tree_golden_deep.npz
+    python tests/golden/make_worker_golden.py 22 deep deep    # tighter tolerances (eps_a 2.3055, eps_r 0.05)
+                                                              # on a depth-5 descendant of root 22
+                                                              # -> worker_tree_golden_deep.npz
+    python tests/golden/make_worker_golden.py 0 config3 config3   # BASELINE config 3: abs_frac 0.03 (eps_a =
+                                                              # 0.27937..., examples.create_oracle) / eps_r
+                                                              # 0.05 on a depth-9 descendant of root 0
+                                                              # -> worker_tree_golden_config3.npz
 """
 import os
 import sys
@@ -37,12 +41,16 @@ EPS_A, EPS_R = 19.21220798973866, 1.0
 def main():
     global ROOT_IDS, EPS_A, EPS_R
     suffix = ''
-    deep = len(sys.argv) > 3 and sys.argv[3] == 'deep'
+    deep = len(sys.argv) > 3 and sys.argv[3] in ('deep', 'config3')
+    depth = 5
     if len(sys.argv) > 1:
         ROOT_IDS = [int(x) for x in sys.argv[1].split(',')]
         suffix = '_' + sys.argv[2]
     if deep:
         EPS_A, EPS_R = 19.21220798973866 / 0.25 * 0.03, 0.05
+        if sys.argv[3] == 'config3':   # eps_a as examples.create_oracle derives it (tools_golden.npz)
+            EPS_A = float(np.load(os.path.join(HERE, 'tools_golden.npz'))['eps_a'][1])
+            depth = 9
     from explicit_hybrid_mpc_b200.mpc_library import InvertedPendulumOnCart
     from oracle.oracle_cpu import CpuOracle
     mpc = InvertedPendulumOnCart()
@@ -65,10 +73,10 @@ def main():
         w.alg_call(which_alg, child, location))
     sys.setrecursionlimit(10000)
     roots = np.load(os.path.join(HERE, 'pendulum_roots.npy'))[ROOT_IDS]
-    if deep:   # a depth-5 descendant, cut with the reference's own split
+    if deep:   # a descendant simplex, cut with the reference's own split
         sub = []
         for R in roots:
-            for d in range(5):
+            for d in range(depth):
                 R = ref_tools.split_along_longest_edge(R)[d % 2]
             sub.append(R)
         roots = np.array(sub)

@@ -114,8 +114,10 @@ def test_worker_recursion_golden(fixture, pendulum, pendulum_roots):
     REFERENCE'S OWN Worker.ecc / Worker.lcss / tools.split_along_longest_edge code
     (lib/worker.py:241-417, imported from /root/reference) built over the six-method oracle API
     (tests/golden/make_worker_golden.py).  The root-0 fixture (2035 nodes) contains a swap-in-place
-    visit (lib/worker.py:396-401); the deep fixture is BASELINE config 3 (abs_frac 0.03 /
-    eps_r 0.05) on a depth-5 descendant of root 22."""
+    visit (lib/worker.py:396-401); the deep fixture uses tighter tolerances (eps_a 2.3055,
+    eps_r 0.05) on a depth-5 descendant of root 22; the config3 fixture is BASELINE config 3 proper
+    (abs_frac 0.03 -> eps_a 0.27937 by examples.create_oracle, eps_r 0.05) on a depth-9 descendant
+    of root 0."""
     from oracle.oracle_cpu import CpuOracle
     z, roots, eps_a, eps_r = worker_fixture(fixture, pendulum_roots)
     cpu = CpuOracle(pendulum.problem, eps_a, eps_r, pendulum.theta_scale)
