@@ -221,3 +221,18 @@ def test_geometry_helpers_match_reference_outputs(pendulum_roots, cpu_oracle):
         for impl in (tools.split_along_longest_edge, cpu_oracle.split_along_longest_edge):
             a, b, c = impl(R)
             assert tuple(c) == tuple(ij) and np.array_equal(a, S1) and np.array_equal(b, S2)
+
+
+def test_eps_a_as_create_oracle_derives_it(pendulum):
+    """examples.create_oracle (lib/examples.py:18-47): eps_a = max over the box vertices v of the
+    MICP optimal cost at abs_frac * v.  Fixture values produced by the reference's own function
+    (tests/golden/make_tools_golden.py); the bench and the tests use the 0.25 value."""
+    import itertools
+    from oracle.oracle_cpu import CpuOracle
+    z = np.load(os.path.join(GOLDEN, 'tools_golden.npz'))
+    assert abs(z['eps_a'][0] - 19.21220798973866) <= 1e-9 * 19.2
+    cpu = CpuOracle(pendulum.problem, 1.0, 1.0, pendulum.theta_scale)
+    box = np.array(list(itertools.product(*[(-s, s) for s in pendulum.theta_scale])))
+    for frac, want in zip((0.25, 0.03), z['eps_a']):
+        got = max(cpu.P_theta(frac * v)[2] for v in box)
+        assert abs(got - want) <= 1e-9 * max(1.0, want)
