@@ -98,7 +98,8 @@ def test_split_matches_reference_rule(cpu_oracle):
         assert mij == ij and np.array_equal(m1, S1) and np.array_equal(m2, S2)
 
 
-WORKER_FIXTURES = ['worker_tree_golden.npz', 'worker_tree_golden_root0.npz', 'worker_tree_golden_deep.npz']
+WORKER_FIXTURES = ['worker_tree_golden.npz', 'worker_tree_golden_root0.npz', 'worker_tree_golden_deep.npz',
+                   'worker_tree_golden_config3.npz']
 
 
 def worker_fixture(name, pendulum_roots):
