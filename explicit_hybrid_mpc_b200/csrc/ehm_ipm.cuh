@@ -5,22 +5,20 @@
 // held entirely in shared memory + registers.  It replaces one `.solve()` of the
 // reference (CVXPY -> MOSEK, lib/oracle.py:131,134,166,169,203,276,305,350).
 //
-// Mapping to the hardware (version 2 -- sized for the instruction cache):
-//   * lane L owns rows L, L+32, ...; G is column-major in shared memory (32 lanes read 32
-//     consecutive doubles: conflict free); the per-row state (slack s, multiplier lam and the
-//     two step vectors) also lives in shared memory so that the row loops can stay ROLLED.
-//     The first version kept that state in registers, which forced a 7x unroll of every
-//     row pass: 25k SASS instructions, and ncu showed the warps stalled on instruction
-//     fetch (stall_no_instruction 5.5 per issue, profiles/README.md).  The hot loop is now
-//     ~1.5k instructions and fits the 32 KB L1.5 instruction cache.
+// Mapping to the hardware (round-1 final; history and ncu findings in profiles/README.md):
+//   * one warp = one problem, one-warp CTAs, 8 per SM at 255 registers.  Lane L owns rows L,
+//     L+32, L+64 of the (pre-solved, compacted) 96-row tile; G is column-major in shared memory
+//     (32 lanes read 32 consecutive doubles: conflict free); the per-row state (slack s,
+//     multiplier lam, 1/s / ds, rc / dl, primal residual) also lives in shared memory so that
+//     the row loops stay ROLLED (a fully unrolled first version was 25k SASS instructions and
+//     stalled on instruction fetch) and handle two rows per trip.
 //   * the normal matrix K = H + G' diag(lam/s) G is accumulated per lane in NV(NV+1)/2
-//     registers (static indices) and combined with a recursive-halving reduce-scatter
-//     (62 shuffles instead of 5*55), exchanged through a 64-double scratch line.
-//   * Cholesky is lane-parallel: lane i holds row i of K in registers, column j is formed
-//     with j shuffle broadcasts; the factor is then replicated into every lane's registers so
-//     that the two triangular solves of the predictor / corrector are shuffle-free.
-//   * predictor and corrector share one code path (a 2-trip loop), step lengths are
-//     warp-shuffle min reductions.
+//     registers and summed over the warp through a 32x33 shared-memory transposition (two
+//     rounds of 32 values; the gap sum s'lam rides along, H is added by the summing lane).
+//   * max / min reductions use two 32-bit REDUX on the bit patterns of non-negative doubles.
+//   * the Cholesky factorisation is computed redundantly by every lane in registers (no
+//     broadcasts), the packed factor is left in shared memory for the triangular solves.
+//   * predictor and corrector share one code path (a 2-trip loop).
 //
 // The numerical method is, by specification, the one of oracle/ehm_oracle.c:qp_solve
 // (Mehrotra predictor-corrector in the CVXOPT/ECOS form: sigma=(1-alpha_aff)^3, residuals
@@ -52,13 +50,6 @@ __device__ __forceinline__ double warp_max(double v)
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
     return v;
 }
-__device__ __forceinline__ double warp_min(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
-    return v;
-}
-
 // max / min over the warp of NON-NEGATIVE doubles (NaN propagates as the largest pattern): the
 // IEEE order of non-negative doubles is the unsigned order of their bit patterns, so two
 // 32-bit REDUX instructions replace a 5-level tree of 64-bit shuffles (~70 SASS instructions).
@@ -77,63 +68,8 @@ __device__ __forceinline__ double warp_min_nonneg(double v)
     return __hiloint2double((int)mh, (int)ml);
 }
 
-__host__ __device__ constexpr int pow2_ge(int x) { return x <= 1 ? 1 : 2 * pow2_ge((x + 1) / 2); }
-
-// Recursive-halving reduce-scatter of P per-lane partials (P a power of two).  After the
-// call lane holds LF = max(P/32,1) fully reduced values v[0..LF) whose global indices start
-// at `base`.
-template <int L, int B>
-struct ReduceScatter {
-    template <int P>
-    static __device__ __forceinline__ void run(double (&v)[P], int lane, int &base)
-    {
-        if constexpr (B >= 1) {
-            if constexpr (L > 1) {
-                constexpr int H = L / 2;
-                const bool up = (lane & B) != 0;
-#pragma unroll
-                for (int i = 0; i < H; ++i) {
-                    const double send = up ? v[i] : v[i + H];
-                    const double keep = up ? v[i + H] : v[i];
-                    v[i] = keep + __shfl_xor_sync(kFull, send, B);
-                }
-                if (up) base += H;
-                ReduceScatter<H, B / 2>::run(v, lane, base);
-            } else {
-                v[0] += __shfl_xor_sync(kFull, v[0], B);
-                ReduceScatter<1, B / 2>::run(v, lane, base);
-            }
-        }
-    }
-};
-
-// Sum P per-lane partials over the warp and leave the first `cnt` sums in out[0..cnt)
-// (shared memory), visible to every lane on return.
-template <int P>
-__device__ __forceinline__ void warp_reduce_to_smem(double (&v)[P], double *out, int cnt, int lane)
-{
-    int base = 0;
-    ReduceScatter<P, 16>::run(v, lane, base);
-    constexpr int LF = (P >= 32) ? P / 32 : 1;
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < LF; ++i)
-        if (base + i < cnt) out[base + i] = v[i];
-    __syncwarp();
-}
-
 // Packed lower-triangular index.
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
-
-// Guarded pivot of the Cholesky factorisation (oracle/ehm_oracle.c:cholesky): returns
-// (sqrt(d), 1/sqrt(d)); a pivot that collapsed below 1e-13 of its own original diagonal
-// freezes the direction.
-__device__ __noinline__ double2 chol_pivot(double d, double d0)
-{
-    if (d <= 1e-13 * d0 || d0 <= 0.0) d = 1e100;
-    const double sd = sqrt(d);
-    return make_double2(sd, 1.0 / sd);
-}
 
 // Per-warp shared-memory block of the solver (offsets in doubles from the block base).
 template <int NV, int MR>
@@ -199,20 +135,6 @@ __device__ __forceinline__ void reduce_all(const double (&v)[P], double *out, do
     constexpr int R0 = CNT < 32 ? CNT : 32;
     reduce_round<R0, P, ADD>(v, 0, out, scr, lane, add);
     if constexpr (CNT > 32) reduce_round<CNT - 32, P, ADD>(v, 32, out, scr, lane, add);
-}
-
-// min over the warp of the fractions num/den (den > 0), compared by cross-multiplication so
-// that the row loops need no division; returns the winning (num, den).
-__device__ __forceinline__ void warp_min_frac(double &num, double &den)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double n2 = __shfl_xor_sync(kFull, num, o), d2 = __shfl_xor_sync(kFull, den, o);
-        if (n2 * den < num * d2) {
-            num = n2;
-            den = d2;
-        }
-    }
 }
 
 // Solve  min 0.5 z'Hz + f'z  s.t.  G z <= h  with one warp.  `w` = base of an IpmWs block:

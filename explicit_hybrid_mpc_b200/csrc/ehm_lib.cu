@@ -39,7 +39,7 @@ constexpr int kWarpsPerCta = 1;   // one problem per one-warp CTA
 #ifndef EHM_CTAS_PER_SM
 #define EHM_CTAS_PER_SM 8
 #endif
-constexpr int kCtasPerSm = EHM_CTAS_PER_SM;   // 8 one-warp CTAs per SM: 255 registers each (no spills; 11 CTAs at 168 registers spilled 1.3 KB per thread and ran 1.5x slower), 19 KB of shared memory each
+constexpr int kCtasPerSm = EHM_CTAS_PER_SM;   // 8 one-warp CTAs per SM: 255 registers each (no spills; 11 CTAs at 168 registers spilled 1.3 KB per thread and ran 1.5x slower), 26 KB of shared memory each
 
 __device__ __forceinline__ long long next_item(DevCounters *cnt, int lane)
 {
