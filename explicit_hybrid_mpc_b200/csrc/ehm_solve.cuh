@@ -20,8 +20,8 @@
 // which include the box rows, with margin TAU_INT satisfies the dropped ones with margin
 // TAU_DROP > TAU_INT; optima are unchanged because the feasible set is).  The surviving rows
 // (34-61 for the pendulum) are compacted with warp ballots, so the solver works on <= 96 rows
-// (MRC = 3 per lane) instead of 224: 3-4x less work per iteration and a 16 KB instead of 31 KB
-// shared-memory tile, i.e. 12 instead of 7 resident warps per SM.
+// (MRC = 3 per lane) instead of 224: 3-4x less work per iteration and 26 KB instead of 31 KB of
+// shared memory per problem (8 resident one-warp CTAs per SM at 255 registers).
 //
 // Candidate tables live in global memory (L2 resident: 60 MB for the pendulum), column-major
 // with the row index fastest so that a warp's load of one column is one coalesced 256 B
