@@ -20,19 +20,22 @@ def simplex_volume(R):
 
 
 def split_along_longest_edge(R):
-    """``lib/tools.py:224-257``: the longest edge is the first maximum, in
+    """``lib/tools.py:224-257``: bisect the simplex with vertex rows ``R`` at the midpoint of its
+    longest edge.  Returns ``(S_1, S_2, (i, j))``: ``S_1`` is R with vertex i replaced by the
+    midpoint, ``S_2`` is R with vertex j replaced.  The edge is the first maximum, in
     ``itertools.combinations`` order, of ``la.norm(R[i]-R[j])`` -- the reference's own formula
     (NumPy evaluates it as the square root of a left-to-right fused-multiply-add chain, which is
     what the CUDA kernels and the CPU oracle restate bit for bit)."""
     R = np.asarray(R, dtype=float)
-    combos = list(itertools.combinations(range(R.shape[0]), 2))
-    idx = int(np.argmax([la.norm(R[i] - R[j]) for i, j in combos]))
-    i, j = combos[idx]
-    v_mid = (R[i] + R[j]) / 2.
-    S_1, S_2 = R.copy(), R.copy()
-    S_1[i] = v_mid
-    S_2[j] = v_mid
-    return S_1, S_2, (i, j)
+    edges = list(itertools.combinations(range(len(R)), 2))
+    lengths = [la.norm(R[i] - R[j]) for i, j in edges]
+    i, j = edges[int(np.argmax(lengths))]
+    halves = []
+    for replaced in (i, j):
+        S = R.copy()
+        S[replaced] = (R[i] + R[j]) / 2.
+        halves.append(S)
+    return halves[0], halves[1], (i, j)
 
 
 def kuhn_triangulation(lower, upper, limit=None):
@@ -84,14 +87,16 @@ def spine_from_simplices(simplices, top_vertices=None):
 
 
 def join_triangulation(cursor, new_tree):
-    """``lib/tools.py:191-222``: append new_tree at the rightmost leaf of cursor."""
-    if cursor.is_leaf():
-        cursor.grow(cursor.data, None)
-        cursor.right = new_tree
-        new_tree.top = False
-        cursor.data = None
-    else:
-        join_triangulation(cursor.right, new_tree)
+    """``lib/tools.py:191-222``: hang ``new_tree`` on the rightmost leaf of ``cursor``'s tree.  That
+    leaf turns into a data-less inner node whose left child keeps its simplex and whose right
+    child is ``new_tree`` (no longer a top)."""
+    node = cursor
+    while not node.is_leaf():
+        node = node.right
+    simplex = node.data
+    node.grow(simplex, None)
+    node.right, node.data = new_tree, None
+    new_tree.top = False
 
 
 def leaves(tree, location=''):
