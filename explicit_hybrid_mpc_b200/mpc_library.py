@@ -233,7 +233,9 @@ class InvertedPendulumOnCart:
 class SyntheticMPLP:
     """Synthetic multiparametric mixed-integer LP (no reference counterpart; SURVEY 8d
     config 5): ``min c_k' z  s.t.  A_k z <= b_k + S_k theta``, z in R^nz, K one-hot modes,
-    N=1, theta in [-1,1]^n.  Seeded with ``numpy.random.default_rng(seed)``."""
+    N=1, theta in [-1,1]^n.  Seeded with ``numpy.random.default_rng(seed)``.  Data only in
+    round 1: the CPU oracle partitions it (tests/test_oracle_golden.py), the CUDA engine has no
+    kernel instantiation for NV = 25 yet (``ehm_problem_create`` rejects the shape)."""
 
     def __init__(self, n=8, nz=16, rows=48, K=4, seed=20260922):
         rng = np.random.default_rng(seed)
@@ -242,6 +244,11 @@ class SyntheticMPLP:
         A = rng.standard_normal((K, rows, nz))
         c = rng.standard_normal((K, nz))
         S = rng.standard_normal((K, rows, n))
+        # every row of S is scaled to l1-norm 0.9: with the slack >= 1 below, z0_k stays strictly
+        # feasible for EVERY theta in [-1,1]^n, i.e. Theta has no infeasible region (plain N(0,1)
+        # entries leave most of the box infeasible for all modes and ECC stops with the reference's
+        # 'STOP, Theta contains infeasible regions')
+        S *= 0.9 / np.abs(S).sum(axis=2, keepdims=True)
         z0 = rng.standard_normal((K, nz))
         b = np.einsum('krz,kz->kr', A, z0) + 1.0 + np.abs(rng.standard_normal((K, rows)))
         # box rows keep every LP bounded: |z_j| <= zmax

@@ -237,3 +237,23 @@ def test_eps_a_as_create_oracle_derives_it(pendulum):
     for frac, want in zip((0.25, 0.03), z['eps_a']):
         got = max(cpu.P_theta(frac * v)[2] for v in box)
         assert abs(got - want) <= 1e-9 * max(1.0, want)
+
+
+def test_synthetic_mplp_partition_cpu():
+    """BASELINE config 5's problem family (synthetic n=8 mp-LP, 4 modes) through the CPU oracle:
+    the data generator is well posed (no infeasible region in [-1,1]^8) and the partition of a few
+    Kuhn simplices closes with leaves that tile them.  (Oracle side only: the CUDA engine has no
+    NV = 25 kernel instantiation in round 1.)"""
+    from explicit_hybrid_mpc_b200.mpc_library import SyntheticMPLP
+    from explicit_hybrid_mpc_b200.tools import kuhn_triangulation, simplex_volume
+    from oracle.oracle_cpu import CpuOracle
+    m = SyntheticMPLP()
+    roots = kuhn_triangulation(-np.ones(8), np.ones(8), limit=3)
+    cpu = CpuOracle(m.problem, 0.03, 0.01, m.theta_scale)
+    r = cpu.partition(roots, nthreads=4)
+    assert r['error'] == 0 and r['nfail'] == 0 and r['nleaves'] > 3
+    leaves = np.nonzero(r['left'] < 0)[0]
+    assert (r['closed'][leaves] == 1).all()
+    vol = sum(simplex_volume(r['vertices'][i]) for i in leaves)
+    want = sum(simplex_volume(R) for R in roots)
+    assert abs(vol - want) <= 1e-9 * want
