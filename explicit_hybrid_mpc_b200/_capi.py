@@ -62,6 +62,16 @@ def lib():
     """Load the shared library (raises if it has not been built)."""
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and 'EHM_LIB_PATH' not in os.environ:
+            # a fresh checkout (the .so is not in git): build it in place once, exactly as
+            # __graft_entry__.build() does.  Still no CPU fallback: if nvcc is absent this raises.
+            import subprocess
+            try:
+                subprocess.check_call(['make', '-s', '-C', os.path.join(os.path.dirname(__file__), 'csrc')])
+            except Exception as ex:
+                raise ImportError('%s is missing and could not be built (%r): run `python -c "import '
+                                  '__graft_entry__ as g; g.build()"` (nvcc, sm_100a). There is no CPU '
+                                  'fallback.' % (LIB_PATH, ex))
         if not os.path.exists(LIB_PATH):
             raise ImportError('%s is missing: run `python -c "import __graft_entry__ as g; '
                               'g.build()"` (nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
