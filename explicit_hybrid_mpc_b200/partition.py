@@ -219,25 +219,51 @@ class _Engine:
             pass
 
 
-def partition(oracle, roots, wave=0, max_nodes=0, max_frontier=0, node_budget=0, verbose=0):
+def partition(oracle, roots, wave=0, max_nodes=0, max_frontier=0, node_budget=0, verbose=0,
+              status_path=None, status_every=8):
     """Run ECC + L-CSS to convergence on the device.
 
     oracle : :class:`explicit_hybrid_mpc_b200.oracle.Oracle`
     roots  : (nroots, n+1, n) array of root simplices (HOST memory; copied to the device,
              the resulting node store is copied back -- both inside this call).
+    status_path : optional file rewritten every ``status_every`` waves with the live counters the
+             reference's scheduler publishes in ``status.txt`` (``lib/scheduler.py:311-333``): closed
+             simplices, queue length, time elapsed -- read from the 104-byte control block, no
+             extra device traffic.
     """
     roots = np.ascontiguousarray(roots, dtype=np.float64)
     assert roots.ndim == 3 and roots.shape[1:] == (oracle.n + 1, oracle.n)
     t0 = time.perf_counter()
     eng = _Engine(oracle, roots, wave, max_nodes, max_frontier, node_budget, verbose)
     try:
-        eng.advance(0)
+        if status_path is None:
+            eng.advance(0)
+        else:
+            while True:
+                left = eng.advance(max(1, int(status_every)))
+                _write_live_status(status_path, eng.stats, time.perf_counter() - t0)
+                if left == 0 or (node_budget > 0 and int(eng.stats.nnodes) >= node_budget):
+                    break
         arr = eng.fetch()
         st = eng.stats_dict()
     finally:
         eng.close()
     st['wall_s'] = time.perf_counter() - t0
     return PartitionResult(arr, st, oracle.pb)
+
+
+def _write_live_status(path, stats, elapsed):
+    with open(path, 'w') as f:
+        f.write('\n'.join([
+            '# overall',
+            'number of tasks queue: %d' % int(stats.open_left),
+            'simplex_count: %d' % int(stats.nleaves),
+            'nodes: %d' % int(stats.nnodes),
+            'max depth: %d' % int(stats.max_depth),
+            'oracle solves: %d' % int(stats.nsolves),
+            'time elapsed [s]: %d' % int(elapsed),
+            'time active (total for all processes [s]): %.0f' % (float(stats.device_ms) * 1e-3),
+        ]) + '\n')
 
 
 def partition_checkpoint(oracle, roots, path, node_budget, wave=0, max_nodes=0, max_frontier=0,
