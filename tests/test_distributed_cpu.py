@@ -144,16 +144,19 @@ def _worker(rank, world, port, q, kw):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('kw', [dict(signal=True), dict(signal=True, deal_depth=2), dict(signal=False)],
-                         ids=['flagged', 'flagged+deal', 'fixed-rounds'])
+@pytest.mark.parametrize('kw', [dict(signal=True), dict(signal=True, deal_depth=2), dict(signal=False),
+                                dict(signal=True, deal_depth=2, world=4)],
+                         ids=['flagged', 'flagged+deal', 'fixed-rounds', 'flagged+deal-world4'])
 def test_partition_distributed_gloo_world2(kw):
+    kw = dict(kw)
+    world = kw.pop('world', 2)
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, kw)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, kw)) for r in range(world)]
     for p in procs:
         p.start()
     out, rounds = q.get(timeout=120)
@@ -209,3 +212,34 @@ def test_overall_status_fields(tmp_path):
     assert o['simplex_count_total'] == int((arr['closed'] == 1).sum()) and o['num_tasks_in_queue'] == 0
     txt = open(str(tmp_path / 'status.txt')).read()
     assert 'volume filled (total [%]): 1.0000e+02' in txt and 'simplex_count: %d' % o['simplex_count_total'] in txt
+
+
+def test_stitch_resolves_forwarding_chains():
+    """A frontier record may be handed on more than once (rank 0 -> 1 -> 2): the node it stood for
+    must end up as ONE node of the merged forest, carrying the sub-tree grown by the last owner."""
+    from explicit_hybrid_mpc_b200.partition import stitch
+
+    def part(rows):
+        # rows: (left, right, root_id, depth, closed, origin_rank, origin_node, a, b)
+        n = len(rows)
+        return dict(left=np.array([r[0] for r in rows], np.int32), right=np.array([r[1] for r in rows], np.int32),
+                    root_id=np.array([r[2] for r in rows], np.int32), depth=np.array([r[3] for r in rows], np.int32),
+                    cand=np.zeros(n, np.int32), closed=np.array([r[4] for r in rows], np.uint8),
+                    vertices=np.array([[[r[7]], [r[8]]] for r in rows], float), vcost=np.zeros((n, 2)),
+                    vinput=np.zeros((n, 2, 1)), origin=np.array([[r[5], r[6]] for r in rows], np.int32).reshape(n, 2))
+    # rank 0: root [0,4] split into [0,2] (kept, closed) and [2,4] (exported -> closed=2)
+    p0 = part([(1, 2, 0, 0, 0, -1, -1, 0, 4), (-1, -1, 0, 1, 1, -1, -1, 0, 2), (-1, -1, 0, 1, 2, -1, -1, 2, 4)])
+    # rank 1: imported (0,2), immediately exported again
+    p1 = part([(-1, -1, 0, 1, 2, 0, 2, 2, 4)])
+    # rank 2: imported (1,0), split into two closed leaves
+    p2 = part([(1, 2, 0, 1, 0, 1, 0, 2, 4), (-1, -1, 0, 2, 1, -1, -1, 2, 3), (-1, -1, 0, 2, 1, -1, -1, 3, 4)])
+    m = stitch([p0, p1, p2])
+    assert len(m['left']) == 5                                   # 7 stored nodes - 2 aliases
+    root = int(np.nonzero(m['depth'] == 0)[0][0])
+    kids = [int(m['left'][root]), int(m['right'][root])]
+    assert sorted(float(m['vertices'][k][0, 0]) for k in kids) == [0.0, 2.0]
+    inner = [k for k in kids if m['left'][k] >= 0][0]            # [2,4] continues on rank 2
+    leaves = sorted((float(m['vertices'][c][0, 0]), float(m['vertices'][c][1, 0]))
+                    for c in (m['left'][inner], m['right'][inner]))
+    assert leaves == [(2.0, 3.0), (3.0, 4.0)]
+    assert (m['closed'][m['left'] < 0] == 1).all() and not (m['closed'] == 2).any()
