@@ -119,3 +119,20 @@ def test_split_bit_exact(n, gpu_oracle, cpu_oracle):
     # empty batch: a no-op, not an error
     _capi.check(_capi.lib().ehm_split_batch(n, 0, Rt.data_ptr(), S1t.data_ptr(), S2t.data_ptr(),
                                             ijt.data_ptr(), None))
+
+
+def test_tstar_against_reference_form_golden(gpu_oracle):
+    """The device epigraph problems against the reference-form known answers of
+    tests/golden/epigraph_golden.json (see tests/test_oracle_golden.py)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    E = json.load(open(os.path.join(GOLDEN, 'epigraph_golden.json')))
+    seen = {}
+    for g in E['cases']:
+        R, Vr = np.array(g['R']), np.array(g['Vr'])
+        key = (R.tobytes(), Vr.tobytes())
+        if key not in seen:
+            seen[key] = gpu_oracle._tstar_all(R, Vr)[0].cpu().numpy()
+        t = seen[key][g['cand']]
+        assert abs(t - g['tstar']) <= 2e-6 * max(1.0, abs(g['tstar'])), (g['cand'], t, g['tstar'])

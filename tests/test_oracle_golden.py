@@ -257,3 +257,25 @@ def test_synthetic_mplp_partition_cpu():
     vol = sum(simplex_volume(r['vertices'][i]) for i in leaves)
     want = sum(simplex_volume(R) for R in roots)
     assert abs(vol - want) <= 1e-9 * want
+
+
+def test_epigraph_problems_reference_form(cpu_oracle):
+    """bar_E / bar_D's per-commutation epigraph optimum t*_c (lib/oracle.py:88-102,285-414):
+    the oracle's condensed 10-variable problem against the REFERENCE-FORM problem -- the
+    reference's own big-M rows over 29 continuous variables + simplex multipliers + the two
+    eps-suboptimality inequalities, solved by SciPy (tests/golden/make_epigraph_golden.py)."""
+    E = json.load(open(os.path.join(GOLDEN, 'epigraph_golden.json')))
+    assert len(E['cases']) >= 30
+    seen = {}
+    for g in E['cases']:
+        R, Vr = np.array(g['R']), np.array(g['Vr'])
+        key = (R.tobytes(), Vr.tobytes())
+        if key not in seen:
+            seen[key] = cpu_oracle.bar_E_delta_R(R, Vr, return_tstar=True)
+        conv, ts = seen[key]
+        t = ts[g['cand']]
+        assert np.isfinite(t), g['cand']
+        assert abs(t - g['tstar']) <= 2e-6 * max(1.0, abs(g['tstar'])), (g['cand'], t, g['tstar'])
+    # the convergence flag is what the t* say: converged <=> no candidate at or below zero
+    for conv, ts in seen.values():
+        assert conv == (not np.any(ts[np.isfinite(ts)] <= 0.0))
