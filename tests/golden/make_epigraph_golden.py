@@ -33,8 +33,9 @@ import make_golden  # noqa: E402
 EPS_A, EPS_R = 19.21220798973866, 1.0
 
 
-def reference_form_tstar(ref, R, Vr, delta):
-    """(t*, theta*, V*) of the epigraph problem in reference-form variables, or None."""
+def reference_form_tstar(ref, R, Vr, delta, with_tau=True):
+    """(t*, theta*, V*, max violation) of the epigraph problem in reference-form variables, or None.
+    with_tau=False: min over the simplex of V alone (lib/oracle.py:75-79, in_variability_ball)."""
     n = R.shape[1]
     ic = ref.icont
     Aub, b0, Aeq, e0 = ref.rows(np.zeros(n), delta)
@@ -54,8 +55,11 @@ def reference_form_tstar(ref, R, Vr, delta):
     G[:len(b0), :nz] = Aub; G[:len(b0), nz:nz + na] = -dBu @ R.T; h[:len(b0)] = b0
     G[len(b0):len(b0) + na, nz:nz + na] = -np.eye(na)                      # alpha >= 0
     r1, r2 = len(b0) + na, len(b0) + na + 1
-    G[r1, nz:nz + na] = -Vr; G[r1, -1] = -1.0; h[r1] = -EPS_A               # tau >= eps_a - bar_V
-    G[r2, nz:nz + na] = -k2 * Vr; G[r2, -1] = -1.0; h[r2] = 0.0             # tau >= -bar_V/(1+eps_r)
+    if with_tau:
+        G[r1, nz:nz + na] = -Vr; G[r1, -1] = -1.0; h[r1] = -EPS_A           # tau >= eps_a - bar_V
+        G[r2, nz:nz + na] = -k2 * Vr; G[r2, -1] = -1.0; h[r2] = 0.0         # tau >= -bar_V/(1+eps_r)
+    else:
+        G[r1, -1] = -1.0; G[r2, -1] = 1.0                                   # tau = 0
     E = np.zeros((len(e0) + 1, N)); d = np.zeros(len(e0) + 1)
     E[:len(e0), :nz] = Aeq; E[:len(e0), nz:nz + na] = -dBe @ R.T; d[:len(e0)] = e0
     E[-1, nz:nz + na] = 1.0; d[-1] = 1.0                                    # sum alpha = 1
@@ -130,9 +134,25 @@ def main():
                                      tstar=g[0], theta_star=g[1], Vstar=g[2], max_violation=g[3],
                                      oracle_tstar=float(ts[c])))
             print(base, depth, c, 'ref-form t* %.8f  oracle %.8f  viol %.1e' % (g[0], ts[c], g[3]))
+    # min over the simplex of V*_delta (first problem of in_variability_ball, lib/oracle.py:220-283)
+    out['minv'] = []
+    for base, depth in ((22, 1), (0, 3), (44, 2), (7, 5), (30, 4)):
+        R = roots[base]
+        for d in range(depth):
+            R = split_along_longest_edge(R)[(d + 1) % 2]
+        dref, vx = cpu.V_R(R)
+        if dref is None:
+            continue
+        c = pb.index_from_commutation(dref)
+        g = reference_form_tstar(ref, R, np.zeros(5), dref, with_tau=False)
+        if g is None:
+            continue
+        mine_v = cpu.min_over_simplex(R, c)
+        out['minv'].append(dict(R=R.tolist(), cand=int(c), minV=g[0], theta_star=g[1], max_violation=g[3]))
+        print('minV', base, depth, c, 'ref-form %.8f  oracle %.8f' % (g[0], mine_v))
     with open(os.path.join(HERE, 'epigraph_golden.json'), 'w') as f:
         json.dump(out, f)
-    print('saved', len(out['cases']), 'cases')
+    print('saved', len(out['cases']), 'cases,', len(out['minv']), 'minV cases')
 
 
 if __name__ == '__main__':

@@ -279,3 +279,8 @@ def test_epigraph_problems_reference_form(cpu_oracle):
     # the convergence flag is what the t* say: converged <=> no candidate at or below zero
     for conv, ts in seen.values():
         assert conv == (not np.any(ts[np.isfinite(ts)] <= 0.0))
+    # min over the simplex of V*_delta (first problem of in_variability_ball, :220-283)
+    assert len(E['minv']) >= 5
+    for g in E['minv']:
+        v = cpu_oracle.min_over_simplex(np.array(g['R']), g['cand'])
+        assert v is not None and abs(v - g['minV']) <= 2e-6 * max(1.0, abs(g['minV']))
