@@ -4,13 +4,22 @@
  * explicit_hybrid_mpc_b200/csrc) never links, imports or calls anything in oracle/.  Only
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
  *
- * PARITY UNPINNED: the reference delegates all arithmetic to CVXPY 1.0.21 -> MOSEK 9.0.87
+ * PINNING.  The reference delegates its arithmetic to CVXPY 1.0.21 -> MOSEK 9.0.87
  * (requirements.txt:1-6, lib/global_vars.py:25), neither of which exists in this container,
- * and ships no tests or golden vectors.  Three of its oracle calls are feasibility MICPs
+ * and ships no tests or golden vectors; three of its oracle calls are feasibility MICPs
  * (objective 0, lib/oracle.py:46,201,347) whose returned commutation is solver-internal.
- * This restatement therefore fixes a documented canonical selection rule (see DESIGN.md
- * "Canonical oracle semantics") and is pinned against independent SciPy/HiGHS solutions of
- * the reference-form problems in tests/golden/.
+ * PARITY WITH MOSEK'S OWN CHOICES IS THEREFORE UNPINNED and this restatement fixes a
+ * documented canonical selection rule (DESIGN.md "Canonical oracle semantics").  Everything
+ * else is pinned against the reference's own code, imported from /root/reference and run
+ * here (generating scripts and fixtures under tests/golden/):
+ *   - problem construction (lib/mpc_library.py:410-554) -> fixed-delta optima, MICP / V_R
+ *     feasibility in reference form (SciPy HiGHS / SLSQP): pendulum_golden.json
+ *   - the eps-suboptimality problems of bar_E / bar_D / in_variability_ball in reference form
+ *     (lib/oracle.py:70-102): epigraph_golden.json
+ *   - Worker.ecc / Worker.lcss / tools.split_along_longest_edge / tree.py run unmodified over
+ *     the six oracle calls: worker_tree_golden*.npz, reproduced node for node
+ *   - tools.delaunay / join_triangulation / simplex_volume, examples.create_oracle's eps_a:
+ *     tools_golden.npz
  *
  * What is restated (reference file:line):
  *   lib/oracle.py:104-139   P_theta          -> ehmo_p_theta
