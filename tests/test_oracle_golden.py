@@ -284,3 +284,21 @@ def test_epigraph_problems_reference_form(cpu_oracle):
     for g in E['minv']:
         v = cpu_oracle.min_over_simplex(np.array(g['R']), g['cand'])
         assert v is not None and abs(v - g['minV']) <= 2e-6 * max(1.0, abs(g['minV']))
+
+
+def test_worker_recursion_golden_ecc_branch():
+    """The ECC split branch (lib/worker.py:264-277: V_R finds no common commutation -> split and
+    recurse with 'ecc'), which the pendulum never takes: the reference's own Worker code on the
+    two-mode toy problem of tests/golden/toy_problem.py against the fused CPU loop."""
+    sys_path_golden = os.path.join(GOLDEN)
+    import sys
+    if sys_path_golden not in sys.path:
+        sys.path.insert(0, sys_path_golden)
+    from toy_problem import TOY_EPS, TOY_ROOT, toy_problem
+    from oracle.oracle_cpu import CpuOracle
+    z = np.load(os.path.join(GOLDEN, 'worker_tree_golden_toy.npz'))
+    assert int((z['cand'] < 0).sum()) >= 5                       # data-less ECC nodes exist
+    cpu = CpuOracle(toy_problem(), TOY_EPS[0], TOY_EPS[1], np.ones(2))
+    r = cpu.partition(TOY_ROOT[None], nthreads=2)
+    assert r['error'] == 0 and r['nfail'] == 0 and r['nleaves'] == int(z['leaf'].sum())
+    check_against_worker_golden(r, z, 1)
