@@ -49,7 +49,3 @@ struct ehm_problem {
     std::vector<double> u_dummy;
 };
 
-namespace ehm {
-// launch helpers implemented in ehm_batch.cu, reused by the partition engine
-int launch_cfg_of(int U, int NX, int rows_total);
-}

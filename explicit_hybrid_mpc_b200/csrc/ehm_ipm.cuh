@@ -1,29 +1,34 @@
 // ehm_ipm.cuh -- warp-level dense primal-dual interior-point solver (sm_100a, fp64).
 //
 // One warp solves one small convex QP/LP
-//        min 0.5 z'Hz + f'z   s.t.  G z <= h            (NV <= 10 variables, <= 32*MR rows)
-// held entirely in shared memory + registers.  It replaces one `.solve()` of the
-// reference (CVXPY -> MOSEK, lib/oracle.py:131,134,166,169,203,276,305,350).
+//        min 0.5 z'Hz + f'z   s.t.  G z <= h            (NV variables, m <= CAP rows)
+// held in shared memory + registers.  It replaces one `.solve()` of the reference
+// (CVXPY -> MOSEK, lib/oracle.py:131,134,166,169,203,276,305,350).
 //
-// Mapping to the hardware (round-1 final; history and ncu findings in profiles/README.md):
-//   * one warp = one problem, one-warp CTAs, 8 per SM at 255 registers.  Lane L owns rows L,
-//     L+32, L+64 of the (pre-solved, compacted) 96-row tile; G is column-major in shared memory
-//     (32 lanes read 32 consecutive doubles: conflict free); the per-row state (slack s,
-//     multiplier lam, 1/s / ds, rc / dl, primal residual) also lives in shared memory so that
-//     the row loops stay ROLLED (a fully unrolled first version was 25k SASS instructions and
-//     stalled on instruction fetch) and handle two rows per trip.
-//   * the normal matrix K = H + G' diag(lam/s) G is accumulated per lane in NV(NV+1)/2
-//     registers and summed over the warp through a 32x33 shared-memory transposition (two
-//     rounds of 32 values; the gap sum s'lam rides along, H is added by the summing lane).
-//   * max / min reductions use two 32-bit REDUX on the bit patterns of non-negative doubles.
-//   * the Cholesky factorisation is computed redundantly by every lane in registers (no
-//     broadcasts), the packed factor is left in shared memory for the triangular solves.
-//   * predictor and corrector share one code path (a 2-trip loop).
+// Mapping to the hardware (round 2, "v11"; history and ncu findings in profiles/README.md):
+//   * one warp = one problem; 4 independent warps per CTA, 4 CTAs per SM (16 problems per SM,
+//     <= 128 registers, <= 14 KB of shared memory per problem).
+//   * the row tile is ROW-major with an even row stride TW = 2*odd: a lane reads its own rows
+//     with conflict-free 128-bit loads; every row carries four extra columns behind its NV
+//     coefficients: a = (lam/s)*rp, w = lam/s, v (corrector term) and h.
+//   * per-row state (s, lam, h, rp, 1/s, ds*dl) lives in REGISTERS: lane L owns rows L, L+32, ...
+//   * the normal matrix K = H + G' diag(w) G is built on the fp64 tensor path:
+//     mma.sync.m8n8k4.f64 (DMMA) over groups of four rows, A = [w*G | a]' and B = G taken from
+//     the same tile loads, accumulators initialised with H.  The extra A row a gives the
+//     predictor's right-hand side G'(w*rp) in the same instructions.  Measured on B200
+//     (scripts/ubench/dmma_bench.cu): DMMA and DFMA share one pipe (37.2 vs 34.1 TFLOP/s, no
+//     overlap), so DMMA buys issue slots (1 instruction per 256 FMA) and registers (2
+//     accumulators per 8x8 block instead of NV(NV+1)/2 per lane), not pipe time.
+//   * Cholesky and the triangular solves are cooperative: lane i owns row i of the factor (in
+//     shared memory, odd stride), pivots / solution components travel by shuffle.  The round-1
+//     version factorised redundantly in every lane's registers (32x the work, 112 registers).
+//   * G'v for the corrector is a lane-serial pass (lane k sums column k over the rows).
 //
-// The numerical method is, by specification, the one of oracle/ehm_oracle.c:qp_solve
+// The numerical method is, by specification, the one of oracle/ehm_oracle.c:qp_solve_x
 // (Mehrotra predictor-corrector in the CVXOPT/ECOS form: sigma=(1-alpha_aff)^3, residuals
 // scaled by 1-sigma, centred start s.lam=1, pivot guard, convergence on primal residual,
-// gap s'lam and the propagated dual residual rho*rd0).  Only the summation order differs.
+// gap s'lam and the propagated dual residual rho*rd0, the measured dual residual as a guard).
+// Only the summation order differs.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -68,215 +73,181 @@ __device__ __forceinline__ double warp_min_nonneg(double v)
     return __hiloint2double((int)mh, (int)ml);
 }
 
-// Packed lower-triangular index.
-__host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+// D(8x8) += A(8x4) * B(4x8), fp64 tensor path.  Fragments: a = A[lane/4][lane%4],
+// b = B[lane%4][lane/4], c0/c1 = C[lane/4][2*(lane%4) + 0/1].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int tile_width(int nv)
+{
+    int t = ((nv + 1) & ~1) + 4;
+    while (t % 2 != 0 || (t / 2) % 2 == 0) ++t;   // even, half of it odd: conflict-free 128-bit row reads
+    return t;
+}
 
 // Per-warp shared-memory block of the solver (offsets in doubles from the block base).
-template <int NV, int MR>
+template <int NV, int CAP>
 struct IpmWs {
-    static constexpr int MRP = 32 * MR;
-    static constexpr int oG = 0;                 // G, column-major [NV][MRP]
-    static constexpr int oH = oG + NV * MRP;     // h
-    static constexpr int oS = oH + MRP;          // slack
-    static constexpr int oL = oS + MRP;          // multiplier
-    static constexpr int oA = oL + MRP;          // rp / ds
-    static constexpr int oB = oA + MRP;          // ds.dl / rc / dl
-    static constexpr int oR = oB + MRP;          // primal residual G z + s - h of the iteration
-    static constexpr int oHs = oR + MRP;         // Hessian NV*NV row-major (zeros for an LP)
-    static constexpr int oF = oHs + NV * NV;     // f (16)
-    static constexpr int oZ = oF + 16;           // z in/out (16)
-    static constexpr int oRed = oZ + 16;         // reduction scratch / packed K / packed L (64)
-    static constexpr int oOut = oRed + 64;       // [0] objective [1] iterations [2] flops (8)
-    static constexpr int oLs = oOut + 8;         // packed Cholesky factor / working matrix (64)
-    static constexpr int oD0 = oLs + 64;         // original diagonal of K (16)
-    static constexpr int oHp = oD0 + 16;         // packed lower triangle of the Hessian (64)
-    static constexpr int oScr = oHp + 64;        // 32 x 33 transposition scratch of the reductions
-    static constexpr int kDoubles = oScr + 32 * 33;
+    static_assert(CAP % 4 == 0, "row capacity must be a multiple of the DMMA k-step");
+    static constexpr int TW = tile_width(NV);    // row stride of the tile
+    static constexpr int cA = (NV + 1) & ~1;     // column a = w * rp (even: a and w are stored as one double2)
+    static constexpr int cW = cA + 1;            // column w = lam / s (on exit: lam)
+    static constexpr int cV = cA + 2;            // column v: corrector term / scratch vector
+    static constexpr int cH = cA + 3;            // column h (right-hand side, never overwritten)
+    static constexpr int NBA = (cA + 1 + 7) / 8; // 8-row blocks of [vars ; (pad) ; a]
+    static constexpr int NBB = (NV + 7) / 8;     // 8-column blocks of the variables
+    static constexpr int LS = 8 * NBB + 1;       // row stride of K / L (odd: lane i reads row i)
+    static constexpr int NVP = 8 * NBB;
+    static constexpr int HS = NV | 1;            // row stride of H (odd)
+    static constexpr int MR = (CAP + 31) / 32;   // row slots per lane
+    static constexpr int oT = 0;                               // tile [CAP][TW] (+ over-read pad)
+    static constexpr int oK = oT + CAP * TW + 8 * NBA;         // K ext [8*NBA][LS]: rows < NV = K / L, row cA = G'(w rp)
+    static constexpr int oHs = oK + 8 * NBA * LS + 1;          // H [NV][HS]
+    static constexpr int oF = (oHs + NV * HS + 1) & ~1;        // f        (NVP)
+    static constexpr int oZ = oF + NVP;                        // z in/out (NVP)
+    static constexpr int oDz = oZ + NVP;                       // dz       (NVP)
+    static constexpr int oOut = oDz + NVP;                     // [0] objective [1] iterations [2] flops [3] flags
+    static constexpr int kDoubles = oOut + 8;
 };
 
-// Warp sums through shared memory.  Up to 32 per-lane values at a time are transposed through
-// a 32x33 scratch: every lane stores its partial of value i at scr[i*33 + lane] (unit stride:
-// conflict free), then lane L adds the 32 partials of value L (addresses L*33 + j: 16 distinct
-// 8-byte banks per half-warp: conflict free) in a depth-5 tree.  No shuffles: a 64-bit shuffle
-// costs ~12 SASS instructions here and the earlier 8-value version of this routine (11 dependent
-// calls per iteration) was 22 % of all stall samples (profiles/README.md).
-constexpr int kScrStride = 33;
-
-// Sum CNT per-lane partials v[base .. base+CNT) over the warp into out[base .. base+CNT).
-template <int CNT, int P, bool ADD = false>
-__device__ __forceinline__ void reduce_round(const double (&v)[P], int base, double *out, double *scr, int lane,
-                                             const double *add = nullptr)
+// acc_k = sum_{r < m} T[r][k] * T[r][col] for k < NV, returned in lane k (all lanes with the same
+// lane % GW hold the same value).  Lanes are split into 32/GW groups that take rows round-robin.
+template <int NV, int CAP>
+__device__ __forceinline__ double gt_vec(const double *__restrict__ T, int col, int m, int lane)
 {
-#pragma unroll
-    for (int i = 0; i < CNT; ++i) scr[i * kScrStride + lane] = v[base + i];
-    __syncwarp();
-    if (lane < CNT) {
-        const double *q = scr + lane * kScrStride;
-        double t[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) t[j] = q[j] + q[j + 16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] += t[j + 8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) t[j] += t[j + 4];
-        const double sum = (t[0] + t[2]) + (t[1] + t[3]);
-        out[base + lane] = ADD ? sum + add[base + lane] : sum;
+    using W = IpmWs<NV, CAP>;
+    constexpr int GW = NV <= 8 ? 8 : (NV <= 16 ? 16 : 32), NG = 32 / GW;
+    const int k = lane % GW, g = lane / GW;
+    double acc = 0.0, acc2 = 0.0;
+    if (k < NV) {
+        int r = g;
+#pragma unroll 2
+        for (; r + NG < m; r += 2 * NG) {
+            acc = fma(T[r * W::TW + k], T[r * W::TW + col], acc);
+            acc2 = fma(T[(r + NG) * W::TW + k], T[(r + NG) * W::TW + col], acc2);
+        }
+        if (r < m) acc = fma(T[r * W::TW + k], T[r * W::TW + col], acc);
     }
-    __syncwarp();
+    acc += acc2;
+#pragma unroll
+    for (int o = GW; o < 32; o <<= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    return acc;
 }
 
-// Sum the first CNT of P per-lane partials over the warp into out[0..CNT) (shared memory).
-// With ADD the constant vector add[0..CNT) is added to the sums (the Hessian joins the normal
-// matrix here, two additions per lane instead of one per entry and lane later).
-template <int CNT, int P, bool ADD = false>
-__device__ __forceinline__ void reduce_all(const double (&v)[P], double *out, double *scr, int lane,
-                                           const double *add = nullptr)
-{
-    constexpr int R0 = CNT < 32 ? CNT : 32;
-    reduce_round<R0, P, ADD>(v, 0, out, scr, lane, add);
-    if constexpr (CNT > 32) reduce_round<CNT - 32, P, ADD>(v, 32, out, scr, lane, add);
-}
-
-// Solve  min 0.5 z'Hz + f'z  s.t.  G z <= h  with one warp.  `w` = base of an IpmWs block:
-// G, h, Hs, f and the primal start z must be filled in; act: bit j set <=> row lane+32*j takes
-// part (normalised, non-constant row); rows that do not take part must hold G = 0, h = 1.
-// On return z holds the solution, out[0..2] the objective / iteration count / algorithmic
-// flops.  returns 0 converged, 1 iteration limit, 2 numerical breakdown.
-//
-// Row passes handle TWO rows per trip of a rolled loop (independent dependency chains: the
-// solver is latency bound with 7 resident warps per SM), are branch free (rows that do not
-// take part carry s = 1, lam = 0 and a zero mask) and contain no division: 1/s is formed once
-// per row and iteration, step-length ratios are compared by cross-multiplication.
+// Solve  min 0.5 z'Hz + f'z  s.t.  G z <= h  with one warp.  `w` = base of an IpmWs block: the
+// tile rows [0, m) (coefficients in columns [0, NV), h in column cH), H (if hasH), f and the
+// primal start z must be filled in.  Rows [m, roundup4(m)) may hold anything finite.
+// On return z holds the solution, column cW of the tile the multipliers, out[0..2] the
+// objective / iteration count / algorithmic flops.
+// returns 0 converged, 1 iteration limit, 2 numerical breakdown.
 //
 // early (warp-uniform): the problem is a phase-1 LP  min sigma : G z - sigma <= h  (sigma = last
 // variable, started strictly feasible, so every iterate is a feasible point of it).  The solve
 // stops as soon as z_k leaves every original row a slack >= TAU_INT: "alive" is then certified
 // (sigma* <= -TAU_INT) and later iterations cannot change the answer (oracle/ehm_oracle.c:
 // qp_solve_x).  The objective returned in that case is the bound -TAU_INT.
-template <int NV, int MR>
-__device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane, bool early = false)
+template <int NV, int CAP>
+__device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, bool early = false)
 {
-    using W = IpmWs<NV, MR>;
-    constexpr int MRP = W::MRP;
-    constexpr int NK = NV * (NV + 1) / 2;
-    constexpr int PK = 8 * ((NK + 8) / 8);   // accumulators + the gap sum, padded to 8-value chunks
-    constexpr int PV = 8 * ((NV + 7) / 8);
-    const double *__restrict__ Gs = w + W::oG;
-    const double *__restrict__ hs = w + W::oH;
-    double *sv = w + W::oS, *lv = w + W::oL, *av = w + W::oA, *bv = w + W::oB, *rv = w + W::oR;
+    using W = IpmWs<NV, CAP>;
+    constexpr int TW = W::TW, MR = W::MR, LS = W::LS, NBA = W::NBA, NBB = W::NBB;
+    constexpr int NVE = NV & ~1;   // even part of the columns (128-bit loads), NV - NVE = 0/1 tail
+    double *T = w + W::oT, *Ks = w + W::oK, *zs = w + W::oZ, *dzs = w + W::oDz;
     const double *__restrict__ Hs = w + W::oHs;
-    double *red = w + W::oRed, *Ls = w + W::oLs, *scr = w + W::oScr, *Hp = w + W::oHp;
-    double z[NV], f[NV];
-    double fmx = 0.0;
+    const double *__restrict__ fs = w + W::oF;
+    // per-row state in registers
+    double s[MR], lam[MR], hh[MR], rp[MR], rs[MR], dsdl[MR];
+    const double fk = lane < NV ? fs[lane] : 0.0;
+    const double fmx = warp_max_nonneg(fabs(fk));
+    double zk = lane < NV ? zs[lane] : 0.0;   // lane k owns z_k
+    const double mact = (double)m;
+    const int ngroups = (m + 3) >> 2;
+    // ---- centred start -------------------------------------------------------------------------
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        f[k] = w[W::oF + k];
-        z[k] = w[W::oZ + k];
-        fmx = fmax(fmx, fabs(f[k]));
-    }
-    const double mact = warp_sum((double)__popc(act));
-    for (int idx = lane; idx < NK; idx += 32) {   // packed lower triangle of H
-        int i = 0;
-        while ((i + 1) * (i + 2) / 2 <= idx) ++i;
-        Hp[idx] = Hs[i * NV + idx - i * (i + 1) / 2];
-    }
-    if (lane == 0) Hp[NK] = 0.0;   // slot of the gap sum s'lam in the reduction
-    // row pairs in which no lane has a participating row are skipped (warp-uniform)
-    unsigned pairs = 0;
+    for (int j = 0; j < MR; ++j) {
+        const int r = lane + 32 * j;
+        s[j] = 1.0; lam[j] = 0.0; hh[j] = 1.0; rp[j] = 0.0; rs[j] = 1.0; dsdl[j] = 0.0;
+        if (r < m) {
+            double gz = 0.0;
 #pragma unroll
-    for (int j = 0; j < MR; j += 2)
-        if (__any_sync(kFull, (act >> j & 3u) != 0u)) pairs |= 1u << j;
-    // ---- centred start + initial dual residual rd0 = |H z0 + f + G' lam0| -----------------
+            for (int k = 0; k < NVE; k += 2) {
+                const double2 g = *reinterpret_cast<const double2 *>(T + r * TW + k);
+                const double2 zz = *reinterpret_cast<const double2 *>(zs + k);
+                gz = fma(g.x, zz.x, fma(g.y, zz.y, gz));
+            }
+            if (NV & 1) gz = fma(T[r * TW + NV - 1], zs[NV - 1], gz);
+            hh[j] = T[r * TW + W::cH];
+            s[j] = fmax(hh[j] - gz, 1.0);
+            lam[j] = 1.0 / s[j];
+            T[r * TW + W::cV] = lam[j];
+        }
+    }
+    __syncwarp();
+    // initial dual residual rd0 = |H z0 + f + G' lam0|
     double rd0;
     {
-        double gl[PV];
-#pragma unroll
-        for (int k = 0; k < PV; ++k) gl[k] = 0.0;
-#pragma unroll 1
-        for (int j = 0; j < MR; ++j) {
-            const int r = lane + 32 * j;
-            if (!(act >> j & 1u)) {
-                sv[r] = 1.0;
-                lv[r] = 0.0;
-                av[r] = 1.0;
-                bv[r] = 0.0;
-                continue;
-            }
-            double g[NV], gz = 0.0;
-#pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                g[k] = Gs[k * MRP + r];
-                gz = fma(g[k], z[k], gz);
-            }
-            const double s = fmax(hs[r] - gz, 1.0);
-            const double l = 1.0 / s;
-            sv[r] = s;
-            lv[r] = l;
-            av[r] = l;
-            bv[r] = 0.0;
-#pragma unroll
-            for (int k = 0; k < NV; ++k) gl[k] = fma(g[k], l, gl[k]);
-        }
-        reduce_all<NV>(gl, red, scr, lane);
-        double m = 0.0;
+        double v = gt_vec<NV, CAP>(T, W::cV, m, lane);
         if (lane < NV) {
-            double hz = w[W::oF + lane] + red[lane];
-#pragma unroll
-            for (int l = 0; l < NV; ++l) hz = fma(Hs[lane * NV + l], z[l], hz);
-            m = fabs(hz);
-        }
-        rd0 = warp_max(m);
-        __syncwarp();
+            v += fk;
+            if (hasH)
+                for (int q = 0; q < NV; ++q) v = fma(Hs[lane * W::HS + q], zs[q], v);
+        } else v = 0.0;
+        rd0 = warp_max_nonneg(fabs(v));
     }
-    // masks of the two rows handled per loop trip
     int status = 1, it = 0;
     double rho = 1.0, obj = 0.0;
 #pragma unroll 1
     for (it = 0; it <= EHM_MAX_ITER; ++it) {
-        // ---- pass A: primal residual, gap, 1/s, normal matrix -------------------------------
-        double acc[PK];
-#pragma unroll
-        for (int k = 0; k < PK; ++k) acc[k] = 0.0;
-        double rpm = 0.0, lmx = 0.0;
-        double &mu_acc = acc[NK];
+        // ---- pass A: primal residual, gap, 1/s, w, a -----------------------------------------
+        double rpm = 0.0, lmx = 0.0, mu = 0.0;
         bool cert = early;
-        const double cthr = EHM_TAU_INT + z[NV - 1];
-#pragma unroll 1
-        for (int j = 0; j < MR; j += 2) {
-            if (!(pairs >> j & 1u)) continue;
-            const bool on1 = (j + 1 < MR);
-            const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
-            // rows that do not take part in THIS solve (e.g. the epigraph rows during phase 1)
-            // may hold data: mask them (their s = 1, lam = 0 already keep K and the gap clean)
-            const double m0 = (act >> j & 1u) ? 1.0 : 0.0;
-            const double m1 = (on1 && (act >> (j + 1) & 1u)) ? 1.0 : 0.0;
-            double g0[NV], g1[NV], gz0 = 0.0, gz1 = 0.0;
+        const double cthr = EHM_TAU_INT + zs[NV - 1];
+        {
+            double gz[MR];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                g0[k] = Gs[k * MRP + r0];
-                g1[k] = Gs[k * MRP + r1];
-                gz0 = fma(g0[k], z[k], gz0);
-                gz1 = fma(g1[k], z[k], gz1);
+            for (int j = 0; j < MR; ++j) gz[j] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NVE; k += 2) {
+                const double2 zz = *reinterpret_cast<const double2 *>(zs + k);
+#pragma unroll
+                for (int j = 0; j < MR; ++j) {
+                    const int r = lane + 32 * j;
+                    if (32 * j < m) {
+                        const double2 g = *reinterpret_cast<const double2 *>(T + (r < CAP ? r : 0) * TW + k);
+                        gz[j] = fma(g.x, zz.x, fma(g.y, zz.y, gz[j]));
+                    }
+                }
             }
-            const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0] * m0, l1 = lv[r1] * m1;
-            const double rs0 = 1.0 / s0, rs1 = 1.0 / s1;
-            av[r0] = rs0;
-            if (on1) av[r1] = rs1;
-            const double rp0 = gz0 + s0 - hs[r0], rp1 = gz1 + s1 - hs[r1];
-            rv[r0] = rp0;
-            if (on1) rv[r1] = rp1;
-            rpm = fmax(rpm, fmax(m0 * fabs(rp0), m1 * fabs(rp1)));
-            // slack of the original row (without the sigma column) at z_k: h - Gz - sigma_k
-            cert = cert && (m0 == 0.0 || s0 - rp0 >= cthr) && (m1 == 0.0 || s1 - rp1 >= cthr);
-            mu_acc = fma(s0, l0, fma(s1, l1, mu_acc));
-            lmx = fmax(lmx, fmax(l0, l1));
-            const double wt0 = l0 * rs0, wt1 = l1 * rs1;
+            if (NV & 1) {
+                const double zl = zs[NV - 1];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                const double gw0 = wt0 * g0[k], gw1 = wt1 * g1[k];
+                for (int j = 0; j < MR; ++j) {
+                    const int r = lane + 32 * j;
+                    if (32 * j < m) gz[j] = fma(T[(r < CAP ? r : 0) * TW + NV - 1], zl, gz[j]);
+                }
+            }
 #pragma unroll
-                for (int q = 0; q <= k; ++q)
-                    acc[tri(k, q)] = fma(gw0, g0[q], fma(gw1, g1[q], acc[tri(k, q)]));
+            for (int j = 0; j < MR; ++j) {
+                const int r = lane + 32 * j;
+                if (32 * j < m && r < 4 * ngroups) {
+                    double a = 0.0, wt = 0.0;
+                    if (r < m) {
+                        rp[j] = gz[j] + s[j] - hh[j];
+                        rs[j] = __drcp_rn(s[j]);
+                        wt = lam[j] * rs[j];
+                        a = wt * rp[j];
+                        rpm = fmax(rpm, fabs(rp[j]));
+                        // slack of the original row (without the sigma column) at z_k: h - Gz - sigma_k
+                        cert = cert && (s[j] - rp[j] >= cthr);
+                        mu = fma(s[j], lam[j], mu);
+                        lmx = fmax(lmx, lam[j]);
+                    }
+                    *reinterpret_cast<double2 *>(T + r * TW + W::cA) = make_double2(a, wt);
+                }
             }
         }
         if (early && __all_sync(kFull, cert)) {
@@ -286,177 +257,205 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane, bool ea
         }
         rpm = warp_max_nonneg(rpm);
         lmx = warp_max_nonneg(lmx);
-        // (H z + f): lane k forms row k, exchanged through the scratch line
-        double hzf[NV], zm;
-        {
-            if (lane < NV) {
-                double v = w[W::oF + lane];
-#pragma unroll
-                for (int q = 0; q < NV; ++q) v = fma(Hs[lane * NV + q], z[q], v);
-                red[lane] = v;
-            }
-            __syncwarp();
-            zm = 0.0;
-            obj = 0.0;
-#pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                hzf[k] = red[k];
-                obj = fma(z[k], 0.5 * (hzf[k] + f[k]), obj);
-                zm = fmax(zm, fabs(z[k]));
-            }
-            __syncwarp();
+        mu = warp_sum(mu);
+        // (H z + f)_k in lane k, objective, |z|
+        double hzf = fk;
+        if (hasH && lane < NV) {
+#pragma unroll 4
+            for (int q = 0; q < NV; ++q) hzf = fma(Hs[lane * W::HS + q], zs[q], hzf);
         }
-        // K (+H) and the gap sum -> red; Cholesky input stays there until it is loaded below
-        reduce_all<NK + 1, PK, true>(acc, red, scr, lane, Hp);
-        const double mu = red[NK];
-        {
-            if (!isfinite(mu) || !isfinite(rpm) || !isfinite(obj)) {
-                status = 2;
-                break;
-            }
-            if (rpm <= EHM_TOL_IPM * (1.0 + zm) && rho * rd0 <= EHM_TOL_IPM * (1.0 + fmx + lmx) &&
-                mu <= EHM_TOL_IPM * (1.0 + fabs(obj))) {
-                status = 0;
-                break;
-            }
+        obj = warp_sum(lane < NV ? zk * 0.5 * (hzf + fk) : 0.0);
+        const double zm = warp_max_nonneg(fabs(zk));
+        if (!isfinite(mu) || !isfinite(rpm) || !isfinite(obj)) {
+            status = 2;
+            break;
         }
+        const bool conv = rpm <= EHM_TOL_IPM * (1.0 + zm) && rho * rd0 <= EHM_TOL_IPM * (1.0 + fmx + lmx) &&
+                          mu <= EHM_TOL_IPM * (1.0 + fabs(obj));
         if (g_trace_on && lane == 0 && it < 120) {
             g_trace[8 * it + 0] = it; g_trace[8 * it + 1] = rpm; g_trace[8 * it + 2] = mu;
             g_trace[8 * it + 3] = obj; g_trace[8 * it + 4] = rho * rd0; g_trace[8 * it + 5] = lmx;
             g_trace[8 * it + 6] = mact; g_trace[8 * it + 7] = NV;
         }
+        if (conv) {
+            // guard on the MEASURED dual residual |Hz + f + G'lam| (it carries the round-off of the
+            // normal equations, so it cannot be held to TOL_IPM; see oracle/ehm_oracle.c)
+#pragma unroll
+            for (int j = 0; j < MR; ++j) {
+                const int r = lane + 32 * j;
+                if (r < m) T[r * TW + W::cV] = lam[j];
+            }
+            __syncwarp();
+            double v = gt_vec<NV, CAP>(T, W::cV, m, lane);
+            v = lane < NV ? fabs(v + hzf) : 0.0;
+            const double rdm = warp_max_nonneg(v);
+            if (rdm <= EHM_TOL_RD * (1.0 + fmx + lmx)) {
+                status = 0;
+                break;
+            }
+        }
         if (it == EHM_MAX_ITER) break;
         const double mu_mean = mu / mact;
-        // ---- K -> packed scratch -> Cholesky, redundantly in every lane's registers (SIMT makes
-        //      the redundancy free; the lane-parallel shuffle version cost 1.5k instructions:
-        //      a 64-bit shuffle is ~13 SASS instructions) -> packed factor in shared memory -----
-        double inv[NV];
+        __syncwarp();
+        // ---- K ext = [H + G'WG ; (G'(w rp))'] on the fp64 tensor path ---------------------------
         {
-            double Lk[NK];
+            double c[NBA][NBB][2];
+            const int cr = lane >> 2, cc = 2 * (lane & 3);
 #pragma unroll
-            for (int i = 0; i < NV; ++i)
+            for (int a = 0; a < NBA; ++a)
 #pragma unroll
-                for (int q = 0; q <= i; ++q) Lk[tri(i, q)] = red[tri(i, q)];
-            __syncwarp();
-            bool bad = false;
+                for (int b = 0; b < NBB; ++b) {
+                    c[a][b][0] = c[a][b][1] = 0.0;
+                    if (hasH && b <= a) {
+                        const int i = 8 * a + cr, q = 8 * b + cc;
+                        if (i < NV && q < NV) c[a][b][0] = Hs[i * W::HS + q];
+                        if (i < NV && q + 1 < NV) c[a][b][1] = Hs[i * W::HS + q + 1];
+                    }
+                }
+            const double *tp = T + (lane & 3) * TW + (lane >> 2);
+#pragma unroll 2
+            for (int g = 0; g < ngroups; ++g, tp += 4 * TW) {
+                double x[NBA];
 #pragma unroll
+                for (int a = 0; a < NBA; ++a) x[a] = tp[8 * a];
+                const double wr = T[(4 * g + (lane & 3)) * TW + W::cW];
+                double aw[NBA];
+#pragma unroll
+                for (int a = 0; a < NBA; ++a) aw[a] = (8 * a + (lane >> 2) < NV) ? x[a] * wr : x[a];
+#pragma unroll
+                for (int a = 0; a < NBA; ++a)
+#pragma unroll
+                    for (int b = 0; b < NBB; ++b)
+                        if (b <= a) dmma884(c[a][b][0], c[a][b][1], aw[a], x[b]);
+            }
+#pragma unroll
+            for (int a = 0; a < NBA; ++a)
+#pragma unroll
+                for (int b = 0; b < NBB; ++b)
+                    if (b <= a) {
+                        double *q = Ks + (8 * a + cr) * LS + 8 * b + cc;
+                        q[0] = c[a][b][0];
+                        q[1] = c[a][b][1];
+                    }
+        }
+        __syncwarp();
+        const double ak = lane < NV ? Ks[W::cA * LS + lane] : 0.0;   // (G'(w rp))_k
+        // ---- Cholesky, lane i = row i, left-looking, in place ------------------------------------
+        double myinv = 1.0;
+        bool bad = false;
+        {
+            const double *rowi = Ks + (lane < NV ? lane : 0) * LS;
+#pragma unroll 1
             for (int j = 0; j < NV; ++j) {
-                const double d0 = Lk[tri(j, j)];
-                double d = d0;
-#pragma unroll
-                for (int k = 0; k < j; ++k) d = fma(-Lk[tri(j, k)], Lk[tri(j, k)], d);
+                const double *rowj = Ks + j * LS;
+                const double d0 = rowj[j];
+                double v = rowi[j];
+                double v2 = 0.0;
+                int k = 0;
+#pragma unroll 2
+                for (; k + 1 < j; k += 2) {
+                    v = fma(-rowi[k], rowj[k], v);
+                    v2 = fma(-rowi[k + 1], rowj[k + 1], v2);
+                }
+                if (k < j) v = fma(-rowi[k], rowj[k], v);
+                v += v2;
+                double d = __shfl_sync(kFull, v, j);
                 if (!isfinite(d)) bad = true;
                 if (d <= 1e-13 * d0 || d0 <= 0.0) d = 1e100;   // pivot guard (oracle: cholesky)
                 const double iv = rsqrt(d);
-                inv[j] = iv;
-                Lk[tri(j, j)] = d * iv;
-#pragma unroll
-                for (int i = j + 1; i < NV; ++i) {
-                    double v = Lk[tri(i, j)];
-#pragma unroll
-                    for (int k = 0; k < j; ++k) v = fma(-Lk[tri(i, k)], Lk[tri(j, k)], v);
-                    Lk[tri(i, j)] = v * iv;
-                }
+                __syncwarp();
+                if (lane >= j && lane < NV) Ks[lane * LS + j] = (lane == j) ? d * iv : v * iv;
+                if (lane == j) myinv = iv;
+                __syncwarp();
             }
-            if (bad) {
-                status = 2;
-                break;
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < NK; ++k) Ls[k] = Lk[k];
-            }
-            __syncwarp();
         }
-        // ---- predictor (trip 0) and corrector (trip 1) share one code path -------------------
-        double sig = 0.0, cres = 1.0, alpha = 1.0;
-        double dz[NV];
+        if (bad) {
+            status = 2;
+            break;
+        }
+        // ---- predictor (trip 0) and corrector (trip 1) --------------------------------------------
+        double sig = 0.0, cres = 1.0, alpha = 1.0, dzk = 0.0;
 #pragma unroll 1
         for (int trip = 0; trip < 2; ++trip) {
-            double rh[PV];
+            double b = 0.0;
+            if (trip == 0) {
+                b = -(hzf + ak);
+            } else {
+                // v = sigma lam + (ds.dl - sigma mu) / s;  rhs = -c (Hz + f + a) + G'v
+                const double smu = sig * mu_mean;
 #pragma unroll
-            for (int k = 0; k < PV; ++k) rh[k] = 0.0;
-#pragma unroll 1
-            for (int j = 0; j < MR; j += 2) {
-                if (!(pairs >> j & 1u)) continue;
-                const bool on1 = (j + 1 < MR);
-                const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
-                const double m0 = (act >> j & 1u) ? 1.0 : 0.0;
-                const double m1 = (on1 && (act >> (j + 1) & 1u)) ? 1.0 : 0.0;
-                double g0[NV], g1[NV];
-#pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    g0[k] = Gs[k * MRP + r0];
-                    g1[k] = Gs[k * MRP + r1];
+                for (int j = 0; j < MR; ++j) {
+                    const int r = lane + 32 * j;
+                    if (r < m) T[r * TW + W::cV] = fma(sig, lam[j], (dsdl[j] - smu) * rs[j]);
                 }
-                const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0], l1 = lv[r1];
-                const double rp0 = rv[r0], rp1 = rv[r1];
-                // rc: s.lam (predictor) or s.lam + ds_aff.dl_aff - sigma mu (corrector)
-                const double rc0 = m0 * (s0 * l0 + (trip ? bv[r0] - sig * mu_mean : 0.0));
-                const double rc1 = m1 * (s1 * l1 + (trip ? bv[r1] - sig * mu_mean : 0.0));
-                if (trip) {
-                    bv[r0] = rc0;
-                    if (on1) bv[r1] = rc1;
-                }
-                // rhs = -c (Hz+f) - G'(c lam + t),  t = (lam c rp - rc)/s
-                const double q0 = m0 * fma(cres, l0, (l0 * cres * rp0 - rc0) * av[r0]);
-                const double q1 = m1 * fma(cres, l1, (l1 * cres * rp1 - rc1) * av[r1]);
-#pragma unroll
-                for (int k = 0; k < NV; ++k) rh[k] = fma(g0[k], q0, fma(g1[k], q1, rh[k]));
+                __syncwarp();
+                const double c1 = gt_vec<NV, CAP>(T, W::cV, m, lane);
+                b = fma(-cres, hzf + ak, c1);
             }
-            reduce_all<NV>(rh, red, scr, lane);
-#pragma unroll
-            for (int k = 0; k < NV; ++k) dz[k] = -cres * hzf[k] - red[k];
+            if (lane >= NV) b = 0.0;
+            // forward  L y = b  (column oriented: y_k travels by shuffle, lane i updates b_i)
+            {
+                const double *rowi = Ks + (lane < NV ? lane : 0) * LS;
+#pragma unroll 1
+                for (int k = 0; k < NV; ++k) {
+                    const double yk = __shfl_sync(kFull, b * myinv, k);
+                    if (lane == k) b = yk;
+                    else if (lane > k && lane < NV) b = fma(-rowi[k], yk, b);
+                }
+                // backward  L' x = y:  x_i final in lane i, lanes k < i subtract L[i][k] x_i
+#pragma unroll 1
+                for (int i = NV - 1; i >= 0; --i) {
+                    const double xi = __shfl_sync(kFull, b * myinv, i);
+                    if (lane == i) b = xi;
+                    else if (lane < i) b = fma(-Ks[i * LS + lane], xi, b);
+                }
+            }
+            dzk = b;
+            if (lane < W::NVP) dzs[lane] = lane < NV ? b : 0.0;
             __syncwarp();
-            // column-oriented triangular solves with the replicated factor (chain length 2/step)
-#pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                dz[k] *= inv[k];
-#pragma unroll
-                for (int i = k + 1; i < NV; ++i) dz[i] = fma(-Ls[tri(i, k)], dz[k], dz[i]);
-            }
-#pragma unroll
-            for (int k = NV - 1; k >= 0; --k) {
-                dz[k] *= inv[k];
-#pragma unroll
-                for (int i = 0; i < k; ++i) dz[i] = fma(-Ls[tri(k, i)], dz[k], dz[i]);
-            }
             // step to the boundary: min over rows of s/(-ds) and lam/(-dl), as fractions
-            double an = 1.0, ad = 1e-300;   // num/den = "infinite" step
-            an = 1e300;
-            ad = 1.0;
-#pragma unroll 1
-            for (int j = 0; j < MR; j += 2) {
-                if (!(pairs >> j & 1u)) continue;
-                const bool on1 = (j + 1 < MR);
-                const int r0 = lane + 32 * j, r1 = on1 ? r0 + 32 : r0;
-                const double m1 = (on1 && (act >> (j + 1) & 1u)) ? 1.0 : 0.0;
-                const double m0 = (act >> j & 1u) ? 1.0 : 0.0;
-                double gd0 = 0.0, gd1 = 0.0;
+            double an = 1e300, ad = 1.0;
+            {
+                double gd[MR];
 #pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    gd0 = fma(Gs[k * MRP + r0], dz[k], gd0);
-                    gd1 = fma(Gs[k * MRP + r1], dz[k], gd1);
-                }
-                const double s0 = sv[r0], s1 = sv[r1], l0 = lv[r0], l1 = lv[r1];
-                const double rp0 = rv[r0], rp1 = rv[r1];
-                const double rc0 = trip ? bv[r0] : s0 * l0, rc1 = trip ? bv[r1] : s1 * l1;
-                const double ds0 = m0 * (-cres * rp0 - gd0), ds1 = m1 * (-cres * rp1 - gd1);
-                const double dl0 = m0 * (-rc0 - l0 * ds0) * av[r0], dl1 = m1 * (-rc1 - l1 * ds1) * av[r1];
-                if (ds0 < 0.0 && s0 * ad < an * (-ds0)) { an = s0; ad = -ds0; }
-                if (dl0 < 0.0 && l0 * ad < an * (-dl0)) { an = l0; ad = -dl0; }
-                if (ds1 < 0.0 && s1 * ad < an * (-ds1)) { an = s1; ad = -ds1; }
-                if (dl1 < 0.0 && l1 * ad < an * (-dl1)) { an = l1; ad = -dl1; }
-                if (trip) {
-                    av[r0] = ds0;
-                    bv[r0] = dl0;
-                    if (on1) {
-                        av[r1] = ds1;
-                        bv[r1] = dl1;
+                for (int j = 0; j < MR; ++j) gd[j] = 0.0;
+#pragma unroll
+                for (int k = 0; k < NVE; k += 2) {
+                    const double2 dd = *reinterpret_cast<const double2 *>(dzs + k);
+#pragma unroll
+                    for (int j = 0; j < MR; ++j) {
+                        const int r = lane + 32 * j;
+                        if (32 * j < m) {
+                            const double2 g = *reinterpret_cast<const double2 *>(T + (r < CAP ? r : 0) * TW + k);
+                            gd[j] = fma(g.x, dd.x, fma(g.y, dd.y, gd[j]));
+                        }
                     }
-                } else {
-                    bv[r0] = ds0 * dl0;
-                    if (on1) bv[r1] = ds1 * dl1;
+                }
+                if (NV & 1) {
+                    const double dl_ = dzs[NV - 1];
+#pragma unroll
+                    for (int j = 0; j < MR; ++j) {
+                        const int r = lane + 32 * j;
+                        if (32 * j < m) gd[j] = fma(T[(r < CAP ? r : 0) * TW + NV - 1], dl_, gd[j]);
+                    }
+                }
+                const double smu = sig * mu_mean;
+#pragma unroll
+                for (int j = 0; j < MR; ++j) {
+                    const int r = lane + 32 * j;
+                    if (r < m) {
+                        const double rc = trip ? fma(s[j], lam[j], dsdl[j] - smu) : s[j] * lam[j];
+                        const double ds = -cres * rp[j] - gd[j];
+                        const double dl = (-rc - lam[j] * ds) * rs[j];
+                        if (ds < 0.0 && s[j] * ad < an * (-ds)) { an = s[j]; ad = -ds; }
+                        if (dl < 0.0 && lam[j] * ad < an * (-dl)) { an = lam[j]; ad = -dl; }
+                        if (trip) {
+                            rp[j] = ds;     // rp / dsdl are dead from here on: they carry the step
+                            dsdl[j] = dl;
+                        } else {
+                            dsdl[j] = ds * dl;
+                        }
+                    }
                 }
             }
             const double amax = warp_min_nonneg(an / ad);
@@ -469,21 +468,27 @@ __device__ __noinline__ int ipm_solve(double *w, unsigned act, int lane, bool ea
             }
         }
         // ---- step ----------------------------------------------------------------------------
+        zk = fma(alpha, dzk, zk);
+        __syncwarp();
+        if (lane < NV) zs[lane] = zk;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) z[k] = fma(alpha, dz[k], z[k]);
-#pragma unroll 1
         for (int j = 0; j < MR; ++j) {
-            if (!(act >> j & 1u)) continue;
             const int r = lane + 32 * j;
-            sv[r] = fma(alpha, av[r], sv[r]);
-            lv[r] = fma(alpha, bv[r], lv[r]);
+            if (r < m) {
+                s[j] = fma(alpha, rp[j], s[j]);
+                lam[j] = fma(alpha, dsdl[j], lam[j]);
+            }
         }
         rho *= 1.0 - alpha * cres;
+        __syncwarp();
     }
     __syncwarp();
-    if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) w[W::oZ + k] = z[k];
+    for (int j = 0; j < MR; ++j) {
+        const int r = lane + 32 * j;
+        if (r < m) T[r * TW + W::cW] = lam[j];
+    }
+    if (lane == 0) {
         w[W::oOut + 0] = obj;
         w[W::oOut + 1] = (double)it;
         // algorithmic flops (2 per FMA): K build m*NV(NV+1), five mat-vec passes 10*m*NV,

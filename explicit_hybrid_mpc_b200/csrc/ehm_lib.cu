@@ -15,31 +15,31 @@ std::atomic<int64_t> g_launches{0};
 using namespace ehm;
 
 // ---------------------------------------------------------------------------------------
-// compiled problem shapes <U, NX, MRI, MRC>: U = N*n_u inputs, NX = n, MR = ceil(rows/32) where
-// rows = N*p + n + 3 (stage rows + simplex rows + two epigraph rows)
+// compiled problem shapes: U = N*n_u inputs, NX = n, CAP = row capacity of the compacted tile
+// (stage rows that survive the pre-solve + n+1 simplex rows + two epigraph rows), WPC warps
+// (= problems) per CTA, CPS CTAs per SM (shared memory per problem: WarpWs<U,NX,CAP>)
 // ---------------------------------------------------------------------------------------
-#define EHM_FOR_EACH_CFG(X) X(0, 5, 4, 7, 3) /* inverted pendulum, N=5: 217 rows in, <= 96 after pre-solve */
+#define EHM_FOR_EACH_CFG(X)                                                                      \
+    X(0, 5, 4, 80, 4, 4)  /* inverted pendulum, N=5: 217 rows in, 41-68 after the pre-solve   */ \
+    X(1, 2, 2, 32, 4, 4)  /* two-mode toy problem of the ECC-split test (tests/golden)        */ \
+    X(2, 16, 8, 96, 1, 5) /* synthetic n=8 mp-LP: 91 rows, NV = 25       */
 
-static int find_cfg(int U, int NX, int rows_total)
+template <int U_, int NX_, int CAP_, int WPC_, int CPS_>
+struct Shape {
+    static constexpr int U = U_, NX = NX_, CAP = CAP_, WPC = WPC_, CPS = CPS_;
+    static constexpr size_t smem = (size_t)WPC_ * WarpWs<U_, NX_, CAP_>::kDoubles * sizeof(double);
+};
+
+static int find_cfg(int U, int NX)
 {
-    const int MR = (rows_total + 31) / 32;
-#define X(ID, UU, NN, MM, CC) \
-    if (U == UU && NX == NN && MR == MM) return ID + 0 * CC;
+#define X(ID, UU, NN, CC, WW, PP) \
+    if (U == UU && NX == NN) return ID;
     EHM_FOR_EACH_CFG(X)
 #undef X
     return -1;
 }
 
 static void ehm_partition_free_now(void *t);   // defined with ehm_partition below
-
-// ---------------------------------------------------------------------------------------
-// kernels
-// ---------------------------------------------------------------------------------------
-constexpr int kWarpsPerCta = 1;   // one problem per one-warp CTA
-#ifndef EHM_CTAS_PER_SM
-#define EHM_CTAS_PER_SM 8
-#endif
-constexpr int kCtasPerSm = EHM_CTAS_PER_SM;   // 8 one-warp CTAs per SM: 255 registers each (no spills; 11 CTAs at 168 registers spilled 1.3 KB per thread and ran 1.5x slower), 26 KB of shared memory each
 
 __device__ __forceinline__ long long next_item(DevCounters *cnt, int lane)
 {
@@ -63,21 +63,22 @@ __device__ __forceinline__ void account(DevCounters *cnt, const SolveOut &o, int
     }
 }
 
-template <int U, int NX, int MRI, int MRC>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
+template <class SH>
+__global__ void __launch_bounds__(32 * SH::WPC, SH::CPS)
 k_point_batch(DevTables tb, int B, const double *__restrict__ theta, const int *__restrict__ cand,
               double *J, double *u0, int *status, DevCounters *cnt)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
+    constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
     for (;;) {
         const long long b = next_item(cnt, lane);
         if (b >= B) break;
         const int c = cand[b];
         SolveOut o{0, 0.0, 0, 0, 0.0};
         if (c >= 0 && c < tb.ncand)
-            o = solve_point<U, NX, MRI, MRC>(tb, c, theta + (size_t)b * NX, ws, u0 ? u0 + (size_t)b * tb.nu : nullptr, lane);
+            o = solve_point<U, NX, CAP>(tb, c, theta + (size_t)b * NX, ws, u0 ? u0 + (size_t)b * tb.nu : nullptr, lane);
         account(cnt, o, lane);
         if (lane == 0) {
             status[b] = o.status;
@@ -87,22 +88,23 @@ k_point_batch(DevTables tb, int B, const double *__restrict__ theta, const int *
     }
 }
 
-template <int U, int NX, int MRI, int MRC>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
+template <class SH>
+__global__ void __launch_bounds__(32 * SH::WPC, SH::CPS)
 k_simplex_batch(DevTables tb, int B, const double *__restrict__ R, const double *__restrict__ Vr,
                 const int *__restrict__ cand, int mode, int with_phase1, double *val, double *sol,
                 int *status, DevCounters *cnt)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
+    constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
     for (;;) {
         const long long b = next_item(cnt, lane);
         if (b >= B) break;
         const int c = cand[b];
         SolveOut o{0, 0.0, 0, 0, 0.0};
         if (c >= 0 && c < tb.ncand)
-            o = solve_simplex<U, NX, MRI, MRC>(tb, c, R + (size_t)b * (NX + 1) * NX,
+            o = solve_simplex<U, NX, CAP>(tb, c, R + (size_t)b * (NX + 1) * NX,
                                          Vr ? Vr + (size_t)b * (NX + 1) : nullptr, mode,
                                          with_phase1 != 0, ws,
                                          sol ? sol + (size_t)b * (NX + 1) : nullptr, lane);
@@ -257,11 +259,11 @@ extern "C" int ehm_problem_create(const ehm_problem_desc *desc, ehm_problem **ou
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(EHM_ECUDA, "no CUDA device: libehm_b200 has no CPU path");
     Condenser cd(*desc);
-    const int cfg = find_cfg(cd.U, cd.n, cd.m + cd.n + 3);
+    const int cfg = find_cfg(cd.U, cd.n);
     if (cfg < 0) {
         char buf[160];
-        snprintf(buf, sizeof buf, "problem shape U=%d n=%d rows=%d has no compiled kernel", cd.U,
-                 cd.n, cd.m + cd.n + 3);
+        snprintf(buf, sizeof buf, "problem shape U=%d n=%d has no compiled kernel (EHM_FOR_EACH_CFG)", cd.U,
+                 cd.n);
         return fail(EHM_EINVAL, buf);
     }
     double nc = 1;
@@ -274,6 +276,12 @@ extern "C" int ehm_problem_create(const ehm_problem_desc *desc, ehm_problem **ou
     tb.n = cd.n; tb.nu = cd.nu; tb.N = cd.N; tb.K = cd.K; tb.p = cd.p;
     tb.U = cd.U; tb.m = cd.m; tb.MP = cd.MP; tb.Y = cd.Y; tb.ncand = ncand;
     tb.eps_a = desc->eps_a; tb.eps_r = desc->eps_r;
+    {
+        bool lp = true;
+        for (int i = 0; i < cd.n * cd.n && lp; ++i) lp = desc->Q[i] == 0.0 && desc->P[i] == 0.0;
+        for (int i = 0; i < cd.nu * cd.nu && lp; ++i) lp = desc->R[i] == 0.0;
+        tb.is_lp = lp ? 1 : 0;
+    }
     const size_t szG = (size_t)ncand * cd.U * cd.MP, szS = (size_t)ncand * cd.n * cd.MP,
                  szg = (size_t)ncand * cd.MP, szM = (size_t)ncand * cd.Y * cd.Y;
     std::vector<double> hG(szG), hS(szS), hg(szg), hr(szg), hM(szM);
@@ -325,10 +333,11 @@ extern "C" int ehm_set_eps(ehm_problem *p, double eps_a, double eps_r)
 
 extern "C" int ehm_num_candidates(const ehm_problem *p) { return p ? p->tb.ncand : 0; }
 
+template <class SH>
 static int grid_for(const ehm_problem *p, long long items)
 {
-    const long long ctas = (items + kWarpsPerCta - 1) / kWarpsPerCta;
-    const long long cap = (long long)p->sm_count * kCtasPerSm;
+    const long long ctas = (items + SH::WPC - 1) / SH::WPC;
+    const long long cap = (long long)p->sm_count * SH::CPS;
     return (int)std::max(1ll, std::min(ctas, cap));
 }
 
@@ -341,14 +350,14 @@ extern "C" int ehm_qp_theta_delta_batch(ehm_problem *p, int B, const double *d_t
     cudaStream_t st = (cudaStream_t)stream;
     EHM_CUDA(cudaMemsetAsync(&p->dcnt->work, 0, sizeof(unsigned long long), st));
     switch (p->cfg) {
-#define X(ID, UU, NN, MM, CC)                                                                     \
+#define X(ID, UU, NN, CC, WW, PP)                                                                 \
     case ID: {                                                                                \
-        auto kern = k_point_batch<UU, NN, MM, CC>;                                                \
-        const size_t sm = (size_t)kWarpsPerCta * WarpWs<UU, NN, MM, CC>::kDoubles * sizeof(double); \
-        int rc = set_smem(kern, sm);                                                          \
+        using SH = Shape<UU, NN, CC, WW, PP>;                                                 \
+        auto kern = k_point_batch<SH>;                                                        \
+        int rc = set_smem(kern, SH::smem);                                                    \
         if (rc) return rc;                                                                    \
-        kern<<<grid_for(p, B), 32 * kWarpsPerCta, sm, st>>>(p->tb, B, d_theta, d_cand, d_J, d_u0, \
-                                                            d_status, p->dcnt);               \
+        kern<<<grid_for<SH>(p, B), 32 * SH::WPC, SH::smem, st>>>(p->tb, B, d_theta, d_cand, d_J, \
+                                                                 d_u0, d_status, p->dcnt);    \
         break;                                                                                \
     }
         EHM_FOR_EACH_CFG(X)
@@ -370,15 +379,15 @@ extern "C" int ehm_simplex_batch(ehm_problem *p, int B, const double *d_R, const
     cudaStream_t st = (cudaStream_t)stream;
     EHM_CUDA(cudaMemsetAsync(&p->dcnt->work, 0, sizeof(unsigned long long), st));
     switch (p->cfg) {
-#define X(ID, UU, NN, MM, CC)                                                                     \
+#define X(ID, UU, NN, CC, WW, PP)                                                                 \
     case ID: {                                                                                \
-        auto kern = k_simplex_batch<UU, NN, MM, CC>;                                              \
-        const size_t sm = (size_t)kWarpsPerCta * WarpWs<UU, NN, MM, CC>::kDoubles * sizeof(double); \
-        int rc = set_smem(kern, sm);                                                          \
+        using SH = Shape<UU, NN, CC, WW, PP>;                                                 \
+        auto kern = k_simplex_batch<SH>;                                                      \
+        int rc = set_smem(kern, SH::smem);                                                    \
         if (rc) return rc;                                                                    \
-        kern<<<grid_for(p, B), 32 * kWarpsPerCta, sm, st>>>(p->tb, B, d_R, d_Vr, d_cand, mode, \
-                                                            with_phase1, d_val, d_sol,        \
-                                                            d_status, p->dcnt);               \
+        kern<<<grid_for<SH>(p, B), 32 * SH::WPC, SH::smem, st>>>(p->tb, B, d_R, d_Vr, d_cand, \
+                                                                 mode, with_phase1, d_val,    \
+                                                                 d_sol, d_status, p->dcnt);   \
         break;                                                                                \
     }
         EHM_FOR_EACH_CFG(X)
@@ -479,7 +488,7 @@ void fill_stats(ehm_partition *t, ehm_partition_stats *stats)
     stats->stage_flops[5] = c1.flops[3] - c0.flops[3]; stats->stage_flops[7] = c1.flops[4] - c0.flops[4];
 }
 
-template <int U, int NX, int MRI, int MRC>
+template <class SH>
 int advance_t(ehm_partition *t, int64_t max_waves, double budget_ms)
 {
     // budget_ms > 0: stop after the first wave that ends past the budget (every wave ends with a
@@ -493,16 +502,17 @@ int advance_t(ehm_partition *t, int64_t max_waves, double budget_ms)
     const DevTables &tb = p->tb;
     const ehm_partition_opts &o = t->opts;
     const int ncand = tb.ncand;
-    const size_t smem = (size_t)kWarpsPerCta * WarpWs<U, NX, MRI, MRC>::kDoubles * sizeof(double);
-    auto kref = k_lcss_ref<U, NX, MRI, MRC>;
-    auto keval = k_lcss_eval<U, NX, MRI, MRC>;
-    auto kpts = k_lcss_points<U, NX, MRI, MRC>;
-    auto kecc = k_ecc_points<U, NX, MRI, MRC>;
+    constexpr int NX = SH::NX;
+    const size_t smem = SH::smem;
+    auto kref = k_lcss_ref<SH>;
+    auto keval = k_lcss_eval<SH>;
+    auto kpts = k_lcss_points<SH>;
+    auto kecc = k_ecc_points<SH>;
     int rc;
     if ((rc = set_smem(kref, smem)) || (rc = set_smem(keval, smem)) || (rc = set_smem(kpts, smem)) ||
         (rc = set_smem(kecc, smem)))
         return rc;
-    const int gsolve = p->sm_count * kCtasPerSm, tsolve = 32 * kWarpsPerCta;
+    const int gsolve = p->sm_count * SH::CPS, tsolve = 32 * SH::WPC;
     const int gaux = p->sm_count * 4, taux = 256;
     cudaStream_t st = 0;
     cudaEvent_t ev0, ev1, sev[8];
@@ -695,8 +705,8 @@ extern "C" int ehm_partition_advance_for(ehm_partition *t, int64_t max_waves, do
     if (!t) return fail(EHM_EINVAL, "null partition");
     int rc;
     switch (t->pb->cfg) {
-#define X(ID, UU, NN, MM, CC) \
-    case ID: rc = advance_t<UU, NN, MM, CC>(t, max_waves, budget_ms); break;
+#define X(ID, UU, NN, CC, WW, PP) \
+    case ID: rc = advance_t<Shape<UU, NN, CC, WW, PP>>(t, max_waves, budget_ms); break;
         EHM_FOR_EACH_CFG(X)
 #undef X
     default: rc = fail(EHM_EINVAL, "no kernel for this problem shape");

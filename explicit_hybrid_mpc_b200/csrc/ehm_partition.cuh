@@ -154,18 +154,19 @@ __global__ void k_pop(Frontier fr, WaveBuf wv, int base, int W, int ncand, Ctl *
 // ------------------------------------------------------------------------------------------
 // k_lcss_ref: t*_ref (no phase 1: delta_ref is feasible at every vertex)
 // ------------------------------------------------------------------------------------------
-template <int U, int NX, int MRI, int MRC>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
+template <class SH>
+__global__ void __launch_bounds__(32 * SH::WPC, SH::CPS)
 k_lcss_ref(DevTables tb, NodeStore ns, WaveBuf wv, int W, Ctl *ctl, DevCounters *cnt)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
+    constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
     for (;;) {
         const long long e = grab(&ctl->cur[0], lane);
         if (e >= W) break;
         const int nd = wv.node[e];
-        const SolveOut o = solve_simplex<U, NX, MRI, MRC>(tb, ns.cand[nd], ns.verts + (size_t)nd * (NX + 1) * NX,
+        const SolveOut o = solve_simplex<U, NX, CAP>(tb, ns.cand[nd], ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, false,
                                                     ws, nullptr, lane);
         account(cnt, o, lane, 1, ns.cand[nd], nd);
@@ -212,20 +213,21 @@ __global__ void k_lcss_items(NodeStore ns, WaveBuf wv, int W, int ncand, Ctl *ct
 // ------------------------------------------------------------------------------------------
 // k_lcss_eval: alive test + epigraph QP per item
 // ------------------------------------------------------------------------------------------
-template <int U, int NX, int MRI, int MRC>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
+template <class SH>
+__global__ void __launch_bounds__(32 * SH::WPC, SH::CPS)
 k_lcss_eval(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
+    constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
     const int nitems = ctl->nitems;
     for (;;) {
         const long long it = grab(&ctl->cur[1], lane);
         if (it >= nitems) break;
         const int2 ec = wv.items[it];
         const int nd = wv.node[ec.x];
-        const SolveOut o = solve_simplex<U, NX, MRI, MRC>(tb, ec.y, ns.verts + (size_t)nd * (NX + 1) * NX,
+        const SolveOut o = solve_simplex<U, NX, CAP>(tb, ec.y, ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, true, ws,
                                                     wv.it_sol + (size_t)it * (NX + 1), lane,
                                                     wv.it_pl + (size_t)it * (NX + 1));
@@ -236,7 +238,10 @@ k_lcss_eval(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
                 wv.tval[ix] = o.val;
                 wv.lb[ix] = f32_down(o.val);
             } else {
-                wv.lb[ix] = INFINITY;  // dead on this simplex (or numerical failure)
+                // certified dead on this simplex: inherited by every descendant.  A numerical
+                // failure (-1) is no certificate: the inherited bound stays and the descendants
+                // evaluate the candidate again (oracle/ehm_oracle.c:ehmo_lcss_eval)
+                if (o.status == 0) wv.lb[ix] = INFINITY;
                 wv.it_pl[(size_t)it * (NX + 1)] = -INFINITY;  // no plane
             }
         }
@@ -334,13 +339,14 @@ __global__ void k_lcss_select(NodeStore ns, WaveBuf wv, int W, int ncand, Ctl *c
 // ------------------------------------------------------------------------------------------
 // k_lcss_points: vertex / midpoint P_theta_delta and min-over-simplex problems
 // ------------------------------------------------------------------------------------------
-template <int U, int NX, int MRI, int MRC>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
+template <class SH>
+__global__ void __launch_bounds__(32 * SH::WPC, SH::CPS)
 k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
+    constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
     const int np = ctl->npitems;
     for (;;) {
         const long long q = grab(&ctl->cur[2], lane);
@@ -349,7 +355,7 @@ k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt
         const int nd = wv.node[pi.e];
         SolveOut o;
         if (pi.i < 0) {
-            o = solve_simplex<U, NX, MRI, MRC>(tb, pi.c, ns.verts + (size_t)nd * (NX + 1) * NX, nullptr,
+            o = solve_simplex<U, NX, CAP>(tb, pi.c, ns.verts + (size_t)nd * (NX + 1) * NX, nullptr,
                                          EHM_SX_MINV, false, ws, nullptr, lane);
             if (lane == 0) {
                 wv.minv[pi.e] = o.val;
@@ -359,7 +365,7 @@ k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt
             const double *th = (pi.i <= NX) ? ns.verts + ((size_t)nd * (NX + 1) + pi.i) * NX
                                             : wv.vmid + (size_t)pi.e * NX;
             const size_t slot = ((size_t)pi.e * (kSelT + 1) + pi.k) * (NX + 2) + pi.i;
-            o = solve_point<U, NX, MRI, MRC>(tb, pi.c, th, ws, wv.ptU + slot * tb.nu, lane);
+            o = solve_point<U, NX, CAP>(tb, pi.c, th, ws, wv.ptU + slot * tb.nu, lane);
             if (lane == 0) {
                 wv.ptJ[slot] = o.val;
                 wv.ptS[slot] = o.status;
@@ -579,13 +585,14 @@ __global__ void k_lcss_final(DevTables tb, NodeStore ns, Frontier fr, WaveBuf wv
 // ------------------------------------------------------------------------------------------
 // ECC (lib/worker.py:241-291): V_R over all candidates, canonical argmin of summed costs
 // ------------------------------------------------------------------------------------------
-template <int U, int NX, int MRI, int MRC>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm)
+template <class SH>
+__global__ void __launch_bounds__(32 * SH::WPC, SH::CPS)
 k_ecc_points(DevTables tb, NodeStore ns, EccBuf eb, int q0, int ne, int centroid, Ctl *ctl, DevCounters *cnt)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
+    constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ws = smem + (size_t)warp * WarpWs<U, NX, MRI, MRC>::kDoubles;
+    double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
     const int ncand = tb.ncand;
     const long long per = centroid ? ncand : (long long)ncand * (NX + 1);
     const long long total = per * ne;
@@ -611,13 +618,13 @@ k_ecc_points(DevTables tb, NodeStore ns, EccBuf eb, int q0, int ne, int centroid
         }
         // theta must live in global/shared memory for solve_point: stage it in the warp's
         // reduction scratch
-        double *thp = ws + WarpWs<U, NX, MRI, MRC>::oV;
+        double *thp = ws + WarpWs<U, NX, CAP>::oW2 + NX;
         if (lane == 0)
             for (int k = 0; k < NX; ++k) thp[k] = th[k];
         __syncwarp();
         const size_t slot = ((size_t)e * ncand + c) * (NX + 2) + i;
         double *up = (i <= NX) ? eb.U + (((size_t)e * ncand + c) * (NX + 1) + i) * tb.nu : nullptr;
-        const SolveOut o = solve_point<U, NX, MRI, MRC>(tb, c, thp, ws, up, lane);
+        const SolveOut o = solve_point<U, NX, CAP>(tb, c, thp, ws, up, lane);
         account(cnt, o, lane, 4);
         if (lane == 0) {
             eb.J[slot] = o.val;

@@ -10,7 +10,8 @@
 // Every problem class runs through ONE instantiation of ipm_solve (point problems NV=U+1,
 // simplex problems NV=U+NX+1): the phase-1 variable sigma, the epigraph variable tau and --
 // where a problem has one variable less -- an inert dummy column (zero coefficients, zero
-// cost; its Cholesky pivot is frozen by the guard) share the last column.
+// cost; its Cholesky pivot is frozen by the guard; it rides for free in the 8-wide DMMA blocks)
+// share the last column.
 //
 // Row pre-solve.  The condensed problems carry every big-M row of the reference
 // (lib/mpc_library.py:529-534): 210 rows for the pendulum, of which ~160 can never bind inside
@@ -19,9 +20,8 @@
 // which is exact for every decision the engine takes (a point that satisfies the kept rows,
 // which include the box rows, with margin TAU_INT satisfies the dropped ones with margin
 // TAU_DROP > TAU_INT; optima are unchanged because the feasible set is).  The surviving rows
-// (34-61 for the pendulum) are compacted with warp ballots, so the solver works on <= 96 rows
-// (MRC = 3 per lane) instead of 224: 3-4x less work per iteration and 26 KB instead of 31 KB of
-// shared memory per problem (8 resident one-warp CTAs per SM at 255 registers).
+// (34-61 for the pendulum) are compacted with warp ballots into the row-major tile of
+// ehm_ipm.cuh (<= CAP rows).
 //
 // Candidate tables live in global memory (L2 resident: 60 MB for the pendulum), column-major
 // with the row index fastest so that a warp's load of one column is one coalesced 256 B
@@ -36,6 +36,7 @@ namespace ehm {
 struct DevTables {
     int n, nu, N, K, p;
     int U, m, MP, Y, ncand;  // U=N*nu, m=N*p, MP = rows padded to 32, Y=U+n+1
+    int is_lp;               // cost has no quadratic part (Q = P = R = 0)
     const double *G;         // [ncand][U][MP]
     const double *S;         // [ncand][n][MP]
     const double *g;         // [ncand][MP]
@@ -44,24 +45,21 @@ struct DevTables {
     double eps_a, eps_r;
 };
 
-// Shared-memory workspace of one warp.  MRI = input row slots per lane (ceil(rows/32) of the
-// un-presolved problem), MRC = row capacity per lane after the pre-solve.
-template <int U, int NX, int MRI, int MRC>
+// Shared-memory workspace of one warp: the solver block of the simplex problems (the point
+// problems reuse it with their own, smaller layout) + the simplex geometry.
+template <int U, int NX, int CAP>
 struct WarpWs {
     static constexpr int NVS = U + NX + 1;
     static constexpr int NVP = U + 1;
-    using WS = IpmWs<NVS, MRC>;
-    using WP = IpmWs<NVP, MRC>;
-    static constexpr int MRP = 32 * MRC;
+    using WS = IpmWs<NVS, CAP>;
+    using WP = IpmWs<NVP, CAP>;
     static constexpr int Y = U + NX + 1;
-    // assembly scratch behind the solver block (cost transform, simplex geometry)
-    static constexpr int oM = WS::kDoubles;         // candidate M, later Mp (Y*Y)
-    static constexpr int oT = oM + Y * Y;           // T (Y*Y)
-    static constexpr int oMT = oT + Y * Y;          // M*T (Y*Y)
-    static constexpr int oR = oMT + Y * Y;          // simplex vertices (NX+1)*NX
-    static constexpr int oE = oR + (NX + 1) * NX;   // E NX*NX
-    static constexpr int oV = oE + NX * NX;         // Vr (NX+1), padded 16
-    static constexpr int kDoubles = oV + 16;
+    static constexpr int oR = WS::kDoubles;          // simplex vertices (NX+1)*NX
+    static constexpr int oE = oR + (NX + 1) * NX;    // E NX*NX
+    static constexpr int oV = oE + NX * NX;          // Vr (NX+1)
+    static constexpr int oW1 = oV + NX + 1;          // M_thth E (NX*NX)
+    static constexpr int oW2 = oW1 + NX * NX;        // M_thth v0 + m_th (NX), theta scratch (NX)
+    static constexpr int kDoubles = (oW2 + 2 * NX + 1) & ~1;
     static_assert(WP::kDoubles <= WS::kDoubles, "point block must fit the simplex block");
 };
 
@@ -73,23 +71,12 @@ struct SolveOut {
     double flops; // algorithmic flops spent (see ipm_solve)
 };
 
-// bit j set <=> row lane+32*j < nrows
-template <int MRC>
-__device__ __forceinline__ unsigned act_of(int nrows, int lane)
-{
-    unsigned a = 0;
-#pragma unroll
-    for (int j = 0; j < MRC; ++j)
-        if (lane + 32 * j < nrows) a |= 1u << j;
-    return a;
-}
-
-template <int NV, int MRC>
-__device__ __forceinline__ int run_ipm(double *ws, unsigned act, int lane, SolveOut &out, double &obj,
+template <int NV, int CAP>
+__device__ __forceinline__ int run_ipm(double *ws, int m, int lane, bool hasH, SolveOut &out, double &obj,
                                        bool early = false)
 {
-    using W = IpmWs<NV, MRC>;
-    const int st = ipm_solve<NV, MRC>(ws, act, lane, early);
+    using W = IpmWs<NV, CAP>;
+    const int st = ipm_solve<NV, CAP>(ws, m, lane, hasH, early);
     obj = ws[W::oOut + 0];
     out.iters += (int)ws[W::oOut + 1];
     out.flops += ws[W::oOut + 2];
@@ -98,33 +85,26 @@ __device__ __forceinline__ int run_ipm(double *ws, unsigned act, int lane, Solve
     return st;
 }
 
-// zero rows [from, 32*MRC) of an NV-column tile (G = 0, h = 1: the ipm_solve contract for rows
-// that do not take part)
-template <int NV, int MRC>
-__device__ __forceinline__ void clear_rows(double *Gs, double *hs, int from, int lane)
+// zero the coefficients of rows [from, roundup4(from)) (the ipm_solve contract: finite data in
+// the partial last DMMA group)
+template <int NV, int CAP>
+__device__ __forceinline__ void clear_tail(double *T, int from, int lane)
 {
-    constexpr int MRP = 32 * MRC;
-#pragma unroll
-    for (int j = 0; j < MRC; ++j) {
-        const int r = lane + 32 * j;
-        if (r >= from) {
-#pragma unroll
-            for (int k = 0; k < NV; ++k) Gs[k * MRP + r] = 0.0;
-            hs[r] = 1.0;
-        }
-    }
+    using W = IpmWs<NV, CAP>;
+    const int to = (from + 3) & ~3;
+    for (int e = lane; e < (to - from) * W::TW; e += 32) T[from * W::TW + e] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------
 // P_theta_delta at one theta for candidate c.   u0 (nu values) written to u0_out.
 // ---------------------------------------------------------------------------------------
-template <int U, int NX, int MRI, int MRC>
+template <int U, int NX, int CAP>
 __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__restrict__ theta,
                                 double *ws, double *u0_out, int lane)
 {
-    using W = typename WarpWs<U, NX, MRI, MRC>::WP;
-    constexpr int MRP = W::MRP, NV = U + 1;
-    double *Gs = ws + W::oG, *hs = ws + W::oH, *Hs = ws + W::oHs, *fs = ws + W::oF, *zs = ws + W::oZ;
+    using W = typename WarpWs<U, NX, CAP>::WP;
+    constexpr int TW = W::TW, NV = U + 1;
+    double *T = ws + W::oT, *Hs = ws + W::oHs, *fs = ws + W::oF, *zs = ws + W::oZ;
     SolveOut out{0, 0.0, 0, 0, 0.0};
     const int MP = tb.MP, m = tb.m, Y = tb.Y;
     const double *Gc = tb.G + (size_t)c * U * MP, *Sc = tb.S + (size_t)c * NX * MP,
@@ -137,8 +117,8 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
     bool viol = false;
     double s0 = 0.0;
 #pragma unroll 1
-    for (int j = 0; j < MRI; ++j) {
-        const int r = lane + 32 * j;
+    for (int r0 = 0; r0 < m; r0 += 32) {
+        const int r = r0 + lane;
         bool keep = false;
         double g[U], hv = 0.0;
 #pragma unroll
@@ -169,33 +149,31 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
         const unsigned bal = __ballot_sync(kFull, keep);
         if (keep) {
             const int pos = cnt + __popc(bal & lt);
-            if (pos < MRP) {
+            if (pos < CAP) {
 #pragma unroll
-                for (int k = 0; k < U; ++k) Gs[k * MRP + pos] = g[k];
-                Gs[U * MRP + pos] = -1.0;
-                hs[pos] = hv;
+                for (int k = 0; k < U; ++k) T[pos * TW + k] = g[k];
+                T[pos * TW + U] = -1.0;
+                T[pos * TW + W::cH] = hv;
             }
             s0 = fmax(s0, -hv);
         }
         cnt += __popc(bal);
     }
     if (__any_sync(kFull, viol)) return out;
-    if (cnt > MRP) {  // capacity of the compacted tile exceeded (never for the shipped examples)
+    if (cnt > CAP) {  // capacity of the compacted tile exceeded (never for the shipped examples)
         out.status = -1;
         return out;
     }
-    clear_rows<NV, MRC>(Gs, hs, cnt, lane);
-    const unsigned act = act_of<MRC>(cnt, lane);
+    clear_tail<NV, CAP>(T, cnt, lane);
     s0 = warp_max(s0);
     // ---- phase 1: min sigma s.t. G u - sigma <= h --------------------------------------
-    for (int e = lane; e < NV * NV; e += 32) Hs[e] = 0.0;
-    if (lane < 16) {
+    if (lane < W::NVP) {
         fs[lane] = (lane == U) ? 1.0 : 0.0;
         zs[lane] = (lane == U) ? s0 + 1.0 : 0.0;
     }
     __syncwarp();
     double obj;
-    int st = run_ipm<NV, MRC>(ws, act, lane, out, obj, true);
+    int st = run_ipm<NV, CAP>(ws, cnt, lane, false, out, obj, true);
     if (st != 0) {
         out.status = -1;
         return out;
@@ -214,16 +192,15 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
             hd = 2.0 * Mc[lane * Y + lane];
         }
         cs = fmax(1.0, warp_max(fmax(fabs(fv), fabs(hd))));
-        if (lane < 16) {
+        if (lane < W::NVP) {
             fs[lane] = (lane < U) ? fv / cs : 0.0;
             zs[lane] = 0.0;
         }
         for (int e = lane; e < NV * NV; e += 32) {
             const int a = e / NV, b = e % NV;
-            Hs[e] = (a < U && b < U) ? 2.0 * Mc[a * Y + b] / cs : 0.0;
+            Hs[a * W::HS + b] = (a < U && b < U) ? 2.0 * Mc[a * Y + b] / cs : 0.0;
         }
-#pragma unroll
-        for (int j = 0; j < MRC; ++j) Gs[U * MRP + lane + 32 * j] = 0.0;
+        for (int r = lane; r < cnt; r += 32) T[r * TW + U] = 0.0;
         cst = Mc[(Y - 1) * Y + Y - 1];
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
@@ -233,7 +210,7 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
         }
         __syncwarp();
     }
-    st = run_ipm<NV, MRC>(ws, act, lane, out, obj);
+    st = run_ipm<NV, CAP>(ws, cnt, lane, tb.is_lp == 0, out, obj);
     if (st != 0) {
         out.status = -1;
         return out;
@@ -259,17 +236,16 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
 // The gradient comes from the KKT multipliers of the stage rows (oracle/ehm_oracle.c:
 // solve_simplex_qp_pl):  dW/dbeta = dV/dbeta + sum_r lam_r a_(r,beta).
 // ---------------------------------------------------------------------------------------
-template <int U, int NX, int MRI, int MRC>
+template <int U, int NX, int CAP>
 __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__restrict__ Rv,
                                   const double *__restrict__ Vr, int mode, bool phase1,
                                   double *ws, double *sol, int lane, float *plane = nullptr)
 {
-    using WW = WarpWs<U, NX, MRI, MRC>;
+    using WW = WarpWs<U, NX, CAP>;
     using W = typename WW::WS;
-    constexpr int MRP = W::MRP, NB = U + NX, NVS = U + NX + 1, Y = WW::Y;
-    double *Gs = ws + W::oG, *hs = ws + W::oH, *Hs = ws + W::oHs, *fs = ws + W::oF, *zs = ws + W::oZ,
-           *Ms = ws + WW::oM, *Ts = ws + WW::oT, *MTs = ws + WW::oMT, *Rs = ws + WW::oR,
-           *Es = ws + WW::oE, *Vs = ws + WW::oV;
+    constexpr int TW = W::TW, NB = U + NX, NVS = U + NX + 1, Y = WW::Y, HS = W::HS;
+    double *T = ws + W::oT, *Hs = ws + W::oHs, *fs = ws + W::oF, *zs = ws + W::oZ, *Rs = ws + WW::oR,
+           *Es = ws + WW::oE, *Vs = ws + WW::oV, *W1 = ws + WW::oW1, *W2 = ws + WW::oW2;
     SolveOut out{0, 0.0, 0, 0, 0.0};
     const int MP = tb.MP, m = tb.m;
     const double *Gc = tb.G + (size_t)c * U * MP, *Sc = tb.S + (size_t)c * NX * MP,
@@ -295,8 +271,8 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
     double s0 = 0.0;
     // ---- stage rows: normalise, pre-solve, compact ------------------------------------------
 #pragma unroll 1
-    for (int j = 0; j < MRI; ++j) {
-        const int r = lane + 32 * j;
+    for (int r0 = 0; r0 < m; r0 += 32) {
+        const int r = r0 + lane;
         bool keep = false;
         double co[NB], hv = 0.0;
 #pragma unroll
@@ -341,11 +317,11 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         const unsigned bal = __ballot_sync(kFull, keep);
         if (keep) {
             const int pos = cnt + __popc(bal & lt);
-            if (pos < MRP) {
+            if (pos < CAP) {
 #pragma unroll
-                for (int k = 0; k < NB; ++k) Gs[k * MRP + pos] = co[k];
-                Gs[NB * MRP + pos] = 0.0;
-                hs[pos] = hv;
+                for (int k = 0; k < NB; ++k) T[pos * TW + k] = co[k];
+                T[pos * TW + NB] = 0.0;
+                T[pos * TW + W::cH] = hv;
             }
             s0 = fmax(s0, -hv);
         }
@@ -354,7 +330,7 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
     if (__any_sync(kFull, viol)) return out;
     // ---- simplex rows (-beta_i <= 0, sum beta <= 1) and the two epigraph rows ---------------
     const int nextra = NX + 1 + (tau ? 2 : 0);
-    if (cnt + nextra > MRP) {
+    if (cnt + nextra > CAP) {
         out.status = -1;
         return out;
     }
@@ -387,30 +363,26 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
             hv = ((lane == NX + 1) ? Vs[0] - tb.eps_a : Vs[0] * k2) * inv;
         }
 #pragma unroll
-        for (int k = 0; k < NB; ++k) Gs[k * MRP + pos] = co[k];
-        Gs[NB * MRP + pos] = last;
-        hs[pos] = hv;
+        for (int k = 0; k < NB; ++k) T[pos * TW + k] = co[k];
+        T[pos * TW + NB] = last;
+        T[pos * TW + W::cH] = hv;
         if (lane <= NX) s0 = fmax(s0, -hv);
     }
     const int total = cnt + nextra, n1rows = cnt + NX + 1;
-    clear_rows<NVS, MRC>(Gs, hs, total, lane);
+    clear_tail<NVS, CAP>(T, total, lane);
     s0 = warp_max(s0);
     __syncwarp();
     double obj;
     if (phase1 || mode == EHM_SX_ALIVE) {
         // sigma column: -1 on the phase-1 rows, restored to 0 afterwards (the epigraph rows keep
-        // their tau coefficient: they sit behind n1rows and are masked out of this solve)
-        const unsigned act1 = act_of<MRC>(n1rows, lane);
-#pragma unroll
-        for (int j = 0; j < MRC; ++j)
-            if (act1 >> j & 1u) Gs[NB * MRP + lane + 32 * j] = -1.0;
-        for (int e = lane; e < NVS * NVS; e += 32) Hs[e] = 0.0;
-        if (lane < 16) {
+        // their tau coefficient: they sit behind n1rows and take no part in this solve)
+        for (int r = lane; r < n1rows; r += 32) T[r * TW + NB] = -1.0;
+        if (lane < W::NVP) {
             fs[lane] = (lane == NB) ? 1.0 : 0.0;
             zs[lane] = (lane == NB) ? s0 + 1.0 : 0.0;
         }
         __syncwarp();
-        const int st = run_ipm<NVS, MRC>(ws, act1, lane, out, obj, true);
+        const int st = run_ipm<NVS, CAP>(ws, n1rows, lane, false, out, obj, true);
         if (st != 0) {
             out.status = -1;
             return out;
@@ -421,59 +393,78 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
             return out;
         }
         if (!(obj <= -EHM_TAU_INT)) return out;
-#pragma unroll
-        for (int j = 0; j < MRC; ++j)
-            if (act1 >> j & 1u) Gs[NB * MRP + lane + 32 * j] = 0.0;
+        for (int r = lane; r < n1rows; r += 32) T[r * TW + NB] = 0.0;
         __syncwarp();
     }
-    // ---- cost in [u; beta; 1]: Mp = T' M T,  [u;theta;1] = T [u;beta;1] ----------------
+    // ---- cost in [u; beta; 1]:  V = x'Mx, x = [u; theta; 1], theta = v0 + E beta ---------------
+    //   H_uu = 2 Muu, H_ub = 2 Mut E, H_bb = 2 E' Mtt E, f_u = 2 (Mut v0 + mu),
+    //   f_b = 2 E' (Mtt v0 + mt), const = v0' Mtt v0 + 2 mt' v0 + m0
     const double *Mc = tb.M + (size_t)c * Y * Y;
-    for (int e = lane; e < Y * Y; e += 32) {
-        Ms[e] = Mc[e];
-        const int a = e / Y, b = e % Y;
-        double t = 0.0;
-        if (a < U) t = (a == b) ? 1.0 : 0.0;
-        else if (a < U + NX) {
-            const int jj = a - U;
-            if (b >= U && b < U + NX) t = Es[jj * NX + (b - U)];
-            else if (b == Y - 1) t = Rs[jj];
-        } else t = (b == Y - 1) ? 1.0 : 0.0;
-        Ts[e] = t;
-    }
-    __syncwarp();
-    for (int e = lane; e < Y * Y; e += 32) {
-        const int a = e / Y, b = e % Y;
-        double v = 0.0;
+    for (int e = lane; e < NX * NX + NX; e += 32) {
+        if (e < NX * NX) {
+            const int a = e / NX, i = e % NX;   // W1[a][i] = sum_j Mtt[a][j] E[j][i]
+            double v = 0.0;
 #pragma unroll
-        for (int k = 0; k < Y; ++k) v = fma(Ms[a * Y + k], Ts[k * Y + b], v);
-        MTs[e] = v;
-    }
-    __syncwarp();
-    for (int e = lane; e < Y * Y; e += 32) {  // Mp into Ms
-        const int a = e / Y, b = e % Y;
-        double v = 0.0;
+            for (int j = 0; j < NX; ++j) v = fma(Mc[(U + a) * Y + U + j], Es[j * NX + i], v);
+            W1[e] = v;
+        } else {
+            const int a = e - NX * NX;          // W2[a] = sum_j Mtt[a][j] v0[j] + mt[a]
+            double v = Mc[(U + a) * Y + Y - 1];
 #pragma unroll
-        for (int k = 0; k < Y; ++k) v = fma(Ts[k * Y + a], MTs[k * Y + b], v);
-        Ms[e] = v;
+            for (int j = 0; j < NX; ++j) v = fma(Mc[(U + a) * Y + U + j], Rs[j], v);
+            W2[a] = v;
+        }
     }
     __syncwarp();
-    const double cst = Ms[(Y - 1) * Y + Y - 1];
-    if (!tau) {
-        double v = 0.0;
-        if (lane < NB) v = fmax(2.0 * fabs(Ms[lane * Y + lane]), 2.0 * fabs(Ms[lane * Y + Y - 1]));
-        cs = fmax(1.0, warp_max(v));
+    double cst = Mc[(Y - 1) * Y + Y - 1];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) cst = fma(Rs[j], W2[j] + Mc[(U + j) * Y + Y - 1], cst);
+    // unscaled H (NB x NB) and f (NB) entries, one per lane and round
+    double fmine = 0.0;
+    if (lane < NB) {
+        if (lane < U) {
+            fmine = Mc[lane * Y + Y - 1];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) fmine = fma(Mc[lane * Y + U + j], Rs[j], fmine);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) fmine = fma(Es[j * NX + lane - U], W2[j], fmine);
+        }
+        fmine *= 2.0;
     }
     for (int e = lane; e < NVS * NVS; e += 32) {
         const int a = e / NVS, b = e % NVS;
-        Hs[e] = (a < NB && b < NB) ? 2.0 * Ms[a * Y + b] / cs : 0.0;
-    }
-    if (lane < 16) {
-        fs[lane] = (lane < NB) ? 2.0 * Ms[lane * Y + Y - 1] / cs : ((lane == NB && tau) ? 1.0 : 0.0);
-        zs[lane] = 0.0;
+        double v = 0.0;
+        if (a < NB && b < NB) {
+            const int lo = a < b ? a : b, hi = a < b ? b : a;
+            if (hi < U) v = Mc[a * Y + b];
+            else if (lo < U) {   // u-beta block: sum_j Mut[lo][j] E[j][hi-U]
+#pragma unroll
+                for (int j = 0; j < NX; ++j) v = fma(Mc[lo * Y + U + j], Es[j * NX + hi - U], v);
+            } else {             // beta-beta block: sum_j E[j][a-U] W1[j][b-U]
+#pragma unroll
+                for (int j = 0; j < NX; ++j) v = fma(Es[j * NX + a - U], W1[j * NX + b - U], v);
+            }
+            v *= 2.0;
+        }
+        Hs[a * HS + b] = v;
     }
     __syncwarp();
-    const unsigned act = act_of<MRC>(total, lane);
-    const int st = run_ipm<NVS, MRC>(ws, act, lane, out, obj);
+    if (!tau) {
+        double v = 0.0;
+        if (lane < NB) v = fmax(fabs(Hs[lane * HS + lane]), fabs(fmine));
+        cs = fmax(1.0, warp_max(v));
+    }
+    {
+        const double ics = 1.0 / cs;
+        for (int e = lane; e < NVS * NVS; e += 32) Hs[(e / NVS) * HS + e % NVS] *= ics;
+        if (lane < W::NVP) {
+            fs[lane] = (lane < NB) ? fmine * ics : ((lane == NB && tau) ? 1.0 : 0.0);
+            zs[lane] = 0.0;
+        }
+    }
+    __syncwarp();
+    const int st = run_ipm<NVS, CAP>(ws, total, lane, tb.is_lp == 0, out, obj);
     if (st != 0) {
         out.status = -1;
         return out;
@@ -481,26 +472,21 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
     out.status = 1;
     out.val = cs * obj + cst;
     if (plane != nullptr && tau) {
-        const double *lv = ws + W::oL;
         double gb[NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) gb[i] = 0.0;
-#pragma unroll 1
-        for (int j = 0; j < MRC; ++j) {
-            const int r = lane + 32 * j;
-            if (r < cnt) {
-                const double l = lv[r];
+        for (int r = lane; r < cnt; r += 32) {
+            const double l = T[r * TW + W::cW];
 #pragma unroll
-                for (int i = 0; i < NX; ++i) gb[i] = fma(l, Gs[(U + i) * MRP + r], gb[i]);
-            }
+            for (int i = 0; i < NX; ++i) gb[i] = fma(l, T[r * TW + U + i], gb[i]);
         }
         double sg = 0.0, p0 = out.val - zs[NB] * cs;
         const double vst = p0;
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
             double v = warp_sum(gb[i]) + fs[U + i];
-#pragma unroll
-            for (int k = 0; k < NVS; ++k) v = fma(Hs[(U + i) * NVS + k], zs[k], v);
+            if (tb.is_lp == 0)
+                for (int k = 0; k < NVS; ++k) v = fma(Hs[(U + i) * HS + k], zs[k], v);
             gb[i] = cs * v;
             sg += fabs(gb[i]);
             p0 = fma(-gb[i], zs[U + i], p0);

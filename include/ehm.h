@@ -36,6 +36,7 @@ extern "C" {
 #define EHM_TAU_INT   1e-7
 #define EHM_TAU_CONST 1e-7
 #define EHM_ZERO_ROW  1e-13
+#define EHM_TOL_RD    1e-3   /* guard on the measured dual residual at convergence (ehm_oracle.h) */
 #define EHM_MAX_ITER  80
 
 typedef struct ehm_problem ehm_problem;

@@ -26,6 +26,8 @@
 #define MAXNV 40
 
 static long g_iters = 0;
+static double g_rdmax_seen = 0; /* diagnostic: largest scaled measured dual residual at convergence */
+double ehmo_rdmax_seen(void) { return g_rdmax_seen; }
 /* Counters are accumulated per thread and flushed once per task / API call: a shared counter
  * bumped in every IPM iteration turns into a cache line bouncing between all cores (it capped
  * the 128-thread host of the GPU box at the throughput of 8 cores). */
@@ -193,10 +195,13 @@ static int qp_solve_x(int nv, int m, const double *H, const double *f, const dou
         /* Every step scales the dual residual by exactly (1 - alpha (1 - sigma)); the value
          * measured above additionally carries the round-off of the normal equations (up to
          * ~1e-4 relative once lam/s spans 20+ orders), so convergence is tested on the
-         * propagated value rho*rd0; the measured one is not used. */
-        (void)rdmax;
+         * propagated value rho*rd0; the measured one is held to the loose guard TOL_RD only (a
+         * point whose measured residual is larger than that is not accepted as converged). */
+        if (rdmax > g_rdmax_seen * (1 + fmax + lmax) && rpmax <= EHMO_TOL_IPM * (1 + zmax) &&
+            rho * rd0 <= EHMO_TOL_IPM * (1 + fmax + lmax) && mu <= EHMO_TOL_IPM * (1 + fabs(obj)))
+            g_rdmax_seen = rdmax / (1 + fmax + lmax); /* diagnostic only (racy across threads) */
         if (rpmax <= EHMO_TOL_IPM * (1 + zmax) && rho * rd0 <= EHMO_TOL_IPM * (1 + fmax + lmax) &&
-            mu <= EHMO_TOL_IPM * (1 + fabs(obj))) {
+            mu <= EHMO_TOL_IPM * (1 + fabs(obj)) && rdmax <= EHMO_TOL_RD * (1 + fmax + lmax)) {
             status = 0;
             break;
         }
@@ -856,14 +861,17 @@ int ehmo_lcss_eval(ehmo_problem *pb, const double *R, const double *Vr, int cref
         int al = alive_on_simplex(pb, c, R);
         res->n_eval++;
         if (al != 1) {
+            /* a numerical failure is NOT a certificate: the inherited bound stays (the reference
+             * blacklists a delta inside one bar_D call only, lib/oracle.py:398-414), so the
+             * descendants evaluate the candidate again; only a certified "dead" is inherited */
             if (al < 0) res->n_fail++;
-            if (lb) lb[c] = INFINITY;
+            else if (lb) lb[c] = INFINITY;
             continue;
         }
         double t;
         if (solve_simplex_qp_pl(pb, c, R, Vr, 1, &t, NULL, pl ? pl + (size_t)c * (n + 1) : NULL) != 0) {
             res->n_fail++;
-            if (lb) lb[c] = INFINITY;
+            if (pl) pl[(size_t)c * (n + 1)] = -INFINITY;
             continue;
         }
         ts[c] = t;

@@ -50,6 +50,8 @@ typedef struct ehmo_problem ehmo_problem;
 #define EHMO_ZERO_ROW  1e-13  /* |coef| below this (relative to the row's natural scale)
                                  makes the row a constant row                                 */
 #define EHMO_TAU_DROP  1e-3   /* row pre-solve margin (normalised rows)                     */
+#define EHMO_TOL_RD    1e-3   /* guard on the MEASURED dual residual |Hz+f+G'lam| at convergence, relative to
+                                 1+|f|+|lam| (it carries the round-off of the normal equations)     */
 #define EHMO_MAX_ITER  80
 
 /* Switched-affine MPC description; array shapes as in
