@@ -2,12 +2,21 @@
 """
 bench.py -- headline benchmark of the B200 explicit-hybrid-MPC partitioning engine.
 
-Metric (BASELINE.json): epsilon-converged leaf simplices partitioned per second.
-Workload (BASELINE.json configs[1]): inverted pendulum (lib/examples.py:120-163), N=5,
-abs_frac=0.25 / eps_r=1.0 (the reference's own pairing, lib/post_process.py:334-338), the 66
-root simplices of tests/golden/pendulum_roots.npy.  One "step" = one complete ECC + L-CSS
-partition of that parameter set (synthetic in the sense that the root simplices are a
-committed fixture; the oracle problems are the reference's pendulum MPC).
+Metric (BASELINE.json): epsilon-converged leaf simplices partitioned per second.  One "step" = one
+complete ECC + L-CSS partition of the workload's parameter set (root simplices are committed /
+deterministic fixtures; the oracle problems are the workload's MPC problem).
+
+Workloads (``--config``, numbering of SURVEY.md section 8d):
+  2  BASELINE configs[1]: inverted pendulum (lib/examples.py:120-163), N=5, abs_frac 0.25 / eps_r 1.0
+     (the reference's own pairing, lib/post_process.py:334-338), 66 Delaunay root simplices.
+     The partition is checked leaf for leaf against the CPU oracle's full-size fixture.
+  3  BASELINE configs[2]: the same pendulum at abs_frac 0.03 / eps_r 0.05 (eps_a = 0.27937 by
+     examples.create_oracle), root simplices 22-25 (the whole Theta at this tolerance is ~6e7 leaves).
+  5  BASELINE configs[4]: synthetic n=8 mp-LP, 4 modes, first 1024 Kuhn simplices of [-1,1]^8,
+     eps tuned to >= 10^6 leaves -- the scaling workload (a job long enough to shard over 8 GPUs).
+Default: config 5 at every N (the configuration the metric "at 1/2/4/8 B200" is quoted on), with the
+configs[1] measurement, its roofline and its parity check reported in the same line under
+"pendulum_config2" at N=1.
 
   value : leaves / device time of the partition loop (CUDA events around the whole loop,
           candidate tables already resident in HBM), max over ranks.
@@ -17,6 +26,7 @@ committed fixture; the oracle problems are the reference's pendulum MPC).
           installable here) on the box's host cores, bounded sample of the same workload.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -29,12 +39,80 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ABS_FRAC, EPS_R = 0.25, 1.0
-EPS_A_FIXTURE = 19.21220798973866   # max_v P_theta(0.25 v).J, recomputed on the GPU at start-up
 METRIC = 'simplices partitioned/sec (eps-converged leaves)'
-# bounded CPU sample: the cheapest root simplices of the workload (by leaf count), as many as keep
-# the host threads busy for ~12 s; the CPU oracle shares the work of ALL sampled roots over all
-# threads (shared LIFO task queue)
+EPS_A_CONFIG2 = 19.21220798973866   # max_v P_theta(0.25 v).J (lib/examples.py:42-46), recomputed on the GPU
+EPS_A_CONFIG3 = 0.27937460888595    # the same for abs_frac 0.03 (tests/golden/tools_golden.npz)
+FP64_NOMINAL_TFLOPS = 37.0          # B200 data sheet (HGX B200: 296 TFLOP/s fp64 per 8 GPUs)
+
+
+# --------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, config):
+        self.config = config
+        if config in (2, 3):
+            from explicit_hybrid_mpc_b200.mpc_library import InvertedPendulumOnCart
+            self.mpc = InvertedPendulumOnCart()
+            allroots = np.load(os.path.join(ROOT, 'tests', 'golden', 'pendulum_roots.npy'))
+            if config == 2:
+                self.abs_frac, self.eps_a, self.eps_r = 0.25, EPS_A_CONFIG2, 1.0
+                self.root_ids = list(range(len(allroots)))
+                self.name = ('pendulum N=5 abs_frac=0.25 eps_r=1.0, 66 Delaunay root simplices '
+                             '(BASELINE.json configs[1])')
+            else:
+                self.abs_frac, self.eps_a, self.eps_r = 0.03, EPS_A_CONFIG3, 0.05
+                self.root_ids = [22, 23, 24, 25]
+                self.name = ('pendulum N=5 abs_frac=0.03 eps_r=0.05 (eps_a=0.27937), root simplices 22-25 of the '
+                             '66 (BASELINE.json configs[2]; the whole Theta is ~6e7 leaves at this tolerance)')
+            self.roots = allroots[self.root_ids]
+            self.max_nodes = 1 << 22
+        elif config == 5:
+            from explicit_hybrid_mpc_b200.mpc_library import SyntheticMPLP
+            from explicit_hybrid_mpc_b200.tools import kuhn_triangulation
+            self.mpc = SyntheticMPLP()
+            self.abs_frac, self.eps_a, self.eps_r = None, 0.01, 0.003
+            self.roots = kuhn_triangulation(-np.ones(8), np.ones(8), limit=1024)
+            self.root_ids = list(range(1024))
+            self.name = ('synthetic n=8 mp-LP (16 inputs, 80 rows, 4 modes, seed 20260922), first 1024 Kuhn '
+                         'simplices of [-1,1]^8, eps_a=0.01 eps_r=0.003 (BASELINE.json configs[4])')
+            self.max_nodes = 24 << 20
+        else:
+            raise SystemExit('unknown --config %r (2, 3 or 5)' % config)
+        self.n, self.nu = self.mpc.problem.n_x, self.mpc.problem.n_u
+
+    def node_bytes(self):
+        n, nu = self.n, self.nu
+        return 5 * 4 + 1 + 8 * ((n + 1) * n + (n + 1) + (n + 1) * nu)
+
+    def cpu_oracle(self):
+        from oracle.oracle_cpu import CpuOracle
+        return CpuOracle(self.mpc.problem, self.eps_a, self.eps_r, self.mpc.theta_scale)
+
+    def cpu_sample(self, threads=None, seconds=12.0):
+        """Bounded sample of the workload for the CPU legs.  config 2: the cheapest root simplices
+        by the leaf count of the oracle's full-size fixture, as many as keep `threads` host threads busy
+        for about `seconds` (rate from a calibration run on the four cheapest: it under-estimates,
+        their small trees cannot feed many threads for long, hence the 1.5).  configs 3 / 5: a fixed
+        prefix of the root list, with a node budget."""
+        if self.config == 5:
+            return list(range(24))
+        if self.config == 3:
+            return [0]          # index into self.roots: root simplex 22
+        p = os.path.join(ROOT, 'tests', 'golden', 'pendulum_full_leafsets.json')
+        cnt = json.load(open(p))['leaves_per_root']
+        order = [int(i) for i in np.argsort(cnt, kind='stable')]
+        if threads is None:
+            return order[:6]
+        cal = cpu_leg(self, threads, order[:4])
+        budget = 1.5 * cal['value'] * seconds          # leaves
+        sample, tot = [], 0
+        for i in order:
+            if len(sample) >= 6 and tot + cnt[i] > budget:
+                break
+            sample.append(i)
+            tot += cnt[i]
+        return sample
 
 
 def _clock_sampler(stop, out, gpu_index):
@@ -85,56 +163,32 @@ def _host_cores():
     return n
 
 
-def _roots():
-    return np.load(os.path.join(ROOT, 'tests', 'golden', 'pendulum_roots.npy'))
-
-
-def _cpu_sample(threads=None, seconds=12.0):
-    """Bounded sample of the workload for the CPU legs: the cheapest root simplices (by leaf
-    count of the committed full-size result) whose estimated work keeps `threads` host threads
-    busy for about `seconds`.  The rate comes from a calibration run on the four cheapest roots
-    (it under-estimates: their small trees cannot feed many threads for long), hence the 1.5."""
-    p = os.path.join(ROOT, 'tests', 'golden', 'pendulum_root_leafcounts.json')
-    if not os.path.exists(p):
-        return [22, 23, 24, 25]
-    meta = json.load(open(p))
-    cnt = meta['leaves_per_root']
-    order = [int(i) for i in np.argsort(cnt, kind='stable')]
-    if threads is None:
-        return order[:6]
-    cal = cpu_leg(threads, order[:4])
-    budget = 1.5 * cal['value'] * seconds          # leaves
-    sample, tot = [], 0
-    for i in order:
-        if len(sample) >= 6 and tot + cnt[i] > budget:
-            break
-        sample.append(i)
-        tot += cnt[i]
-    return sample
-
-
-def cpu_leg(threads, sample):
-    """Time the CPU oracle (kind 'port') on a bounded sample of the workload."""
-    from explicit_hybrid_mpc_b200.mpc_library import InvertedPendulumOnCart
-    from oracle.oracle_cpu import CpuOracle
-    mpc = InvertedPendulumOnCart()
-    orc = CpuOracle(mpc.problem, EPS_A_FIXTURE, EPS_R, mpc.theta_scale)
-    roots = _roots()[sample]
+def cpu_leg(wl, threads, sample):
+    """Time the CPU oracle (kind 'port') on a bounded sample (indices into wl.roots)."""
+    orc = wl.cpu_oracle()
+    roots = wl.roots[sample]
     t0 = time.perf_counter()
     out = orc.partition(roots, nthreads=threads)
     dt = time.perf_counter() - t0
     return dict(leaves=out['nleaves'], seconds=dt, solves=out['nsolves'], threads=threads,
-                value=out['nleaves'] / dt, solves_per_s=out['nsolves'] / dt)
+                value=out['nleaves'] / dt, solves_per_s=out['nsolves'] / dt, nfail=out['nfail'])
+
+
+def _sample_text(wl, sample, r):
+    ids = [wl.root_ids[i] for i in sample]
+    return ('root simplices %s of the same workload (%d leaves, %.1f s on %d threads)'
+            % (ids if len(ids) <= 40 else '%d..%d' % (ids[0], ids[-1]), r['leaves'], r['seconds'], r['threads']))
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    wl = Workload(args.config)
     threads = _host_cores()
-    sample = _cpu_sample(threads)
+    sample = wl.cpu_sample(threads)
     vals, ms = [], []
     for i in range(args.warmup + args.steps):
-        r = cpu_leg(threads, sample if i >= args.warmup else sample[:1])
+        r = cpu_leg(wl, threads, sample if i >= args.warmup else sample[:1])
         if i >= args.warmup:
             vals.append(r)
             ms.append(r['seconds'] * 1e3)
@@ -144,16 +198,83 @@ def run_reference(args, rank, world):
     line = dict(metric=METRIC, value=value, unit='leaves/s', n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=float(np.mean(ms)), higher_is_better=True,
                 scaling='strong', vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
-                config=dict(workload='pendulum N=5 abs_frac=0.25 eps_r=1.0, 66 Delaunay root simplices',
-                            note='CPU restatement of the reference algorithm (MOSEK/CVXPY/mpi4py '
-                                 'not installable); bounded sample of root simplices %s' % sample),
+                config=dict(workload=wl.name, sample=[wl.root_ids[i] for i in sample],
+                            note='CPU restatement of the reference ALGORITHM (oracle/: condensed problems, row '
+                                 'pre-solve, certified pruning -- far faster than the reference\'s CVXPY->MOSEK path, '
+                                 '~10 solves/s/core by lib/post_process.py:328-330, which is not installable here); '
+                                 'each step partitions the bounded sample of root simplices listed in "sample"; the '
+                                 'GPU arm prints the same sample under "same_sample"'),
                 cpu_baseline=dict(value=value, unit='leaves/s', cores=threads, kind='port',
-                                  sample='%d cheapest root simplices (sized by a calibration run), %d leaves, %.1f s/step'
-                                         % (len(sample), vals[-1]['leaves'], vals[-1]['seconds']),
+                                  sample=_sample_text(wl, sample, vals[-1]),
                                   solves_per_s=sum(v['solves'] for v in vals) / secs),
                 e2e=dict(value=value, unit='leaves/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def _peaks():
+    from explicit_hybrid_mpc_b200 import _capi
+    pk, hb = ctypes.c_double(), ctypes.c_double()
+    _capi.check(_capi.lib().ehm_fp64_peak(ctypes.byref(pk)))
+    _capi.check(_capi.lib().ehm_hbm_peak(1 << 30, ctypes.byref(hb)))
+    hbm_peak, hbm_src = 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            hbm_peak = float(json.load(open(p))['hbm_gbs'])
+            hbm_src = 'MEASURED_PEAKS.json'
+        except Exception:
+            pass
+    return pk.value, hb.value, hbm_peak, hbm_src
+
+
+STAGES = ['k_pop', 'k_lcss_ref', 'k_lcss_items', 'k_lcss_eval', 'k_lcss_select', 'k_lcss_points',
+          'k_lcss_final', 'ecc_phase']
+
+
+def _roofline(st, fp64_peak, config):
+    """fp64 roofline of the dominant IPM kernel of the last step."""
+    sm, fl = st['stage_ms'], st['stage_flops']
+    solve = [1, 3, 5, 7]
+    dom = max(solve, key=lambda k: sm[k])
+    ach = fl[dom] / (sm[dom] * 1e-3) / 1e12 if sm[dom] > 0 else 0.0
+    solve_ms = sum(sm[k] for k in solve)
+    solve_fl = sum(fl[k] for k in solve)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp)).get(str(config))
+            if tj:
+                traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
+        except Exception:
+            pass
+    return dict(bound='fp64', kernel='%s (warp-per-problem interior-point solver)' % STAGES[dom], achieved=ach,
+                peak=fp64_peak, unit='TFLOP/s', frac=ach / fp64_peak if fp64_peak else None,
+                frac_of_nominal=ach / FP64_NOMINAL_TFLOPS, nominal_peak=FP64_NOMINAL_TFLOPS,
+                peak_source='in-run DFMA microbenchmark ehm_fp64_peak (MEASURED_PEAKS.json has no fp64 entry); '
+                            'nominal 37 TFLOP/s = B200 data sheet; DMMA alone measured 37.2 TFLOP/s '
+                            '(scripts/ubench/dmma_bench.cu, profiles/README.md)',
+                traffic=traffic, traffic_unit='dram bytes of ONE saturated launch (not per step)',
+                traffic_source=traffic_src,
+                note='fp64 FMA-pipe bound (SURVEY 8d): achieved = algorithmic flops of all launches of the '
+                     'dominant kernel in the last step / their summed CUDA-event time; all IPM kernels together: '
+                     '%.2f TFLOP/s over %.1f ms' % (solve_fl / (solve_ms * 1e-3) / 1e12 if solve_ms else 0.0, solve_ms),
+                stage_ms={STAGES[k]: round(sm[k], 3) for k in range(8)}, dominant_stage=STAGES[dom])
+
+
+def _check_config2(res):
+    """The partition of configs[1] against the CPU oracle's full-size fixture: leaves per root and
+    sha256 of the sorted leaf vertex sets (scripts/make_full_leafsets.py)."""
+    from explicit_hybrid_mpc_b200.partition import leafset_digest
+    fx = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'pendulum_full_leafsets.json')))
+    cnt, dig = leafset_digest(res.left, res.root_id, res.vertices, fx['nroots'])
+    ok = cnt == fx['leaves_per_root'] and dig == fx['sha256_per_root']
+    return dict(fixture='tests/golden/pendulum_full_leafsets.json (CPU oracle, all 66 roots)',
+                leaves=int(sum(cnt)), fixture_leaves=int(fx['nleaves']), leaf_sets_bit_exact=bool(ok))
 
 
 def main():
@@ -162,7 +283,9 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200')
+    ap.add_argument('--config', type=int, default=5, help='workload: 2, 3 or 5 (see module docstring)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the configs[1] block of the default run')
     ap.add_argument('--wave', type=int, default=0, help='frontier entries per wave (0: library default)')
     ap.add_argument('--round-ms', type=float, default=0.0,
                     help='N>1: meet every so many ms instead of on a starvation flag (0: flag)')
@@ -183,41 +306,42 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from explicit_hybrid_mpc_b200 import _capi
-    from explicit_hybrid_mpc_b200.mpc_library import InvertedPendulumOnCart
     from explicit_hybrid_mpc_b200.oracle import Oracle
-    from explicit_hybrid_mpc_b200.partition import partition
+    from explicit_hybrid_mpc_b200.partition import partition, partition_distributed
 
-    mpc = InvertedPendulumOnCart()
-    roots_all = _roots()
-    # eps_a exactly as examples.create_oracle (lib/examples.py:42-46): max over the vertices of
-    # abs_frac * Theta of the MICP optimal cost -- 16 batched P_theta calls on the device
-    import itertools
-    orc = Oracle(mpc, 1.0, 1.0)
-    box = np.array(list(itertools.product(*[(-s, s) for s in mpc.theta_scale])))
-    eps_a = max(orc.P_theta(ABS_FRAC * v)[2] for v in box)
-    assert abs(eps_a - EPS_A_FIXTURE) <= 1e-6 * EPS_A_FIXTURE, eps_a
-    orc.set_eps(eps_a, EPS_R)
-    from explicit_hybrid_mpc_b200.partition import partition_distributed
-    roots = roots_all           # world == 1: everything; world > 1: sharded inside the driver
+    wl = Workload(args.config)
+    orc = Oracle(wl.mpc, 1.0, 1.0)
+    eps_a = wl.eps_a
+    if wl.abs_frac is not None:
+        # eps_a exactly as examples.create_oracle (lib/examples.py:42-46): max over the vertices of
+        # abs_frac * Theta of the MICP optimal cost -- one batched P_theta call on the device
+        import itertools
+        box = np.array(list(itertools.product(*[(-s, s) for s in wl.mpc.theta_scale])))
+        _, Jb, _ = orc.P_theta_batch(wl.abs_frac * box)
+        eps_a = float(Jb.max().item())
+        assert abs(eps_a - wl.eps_a) <= 1e-6 * wl.eps_a, eps_a
+    orc.set_eps(eps_a, wl.eps_r)
+    roots = wl.roots
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
 
-    def step():
+    def step(o=orc, rts=roots, max_nodes=wl.max_nodes):
         flush.fill_(1)                      # evict L2 between timed iterations
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         if world == 1:
-            res = partition(orc, roots, wave=args.wave)
+            res = partition(o, rts, wave=args.wave, max_nodes=max_nodes)
             info = dict(exchange_s=0.0, rounds=0, records_sent=0)
         else:
             # one partition job over all ranks: sharded frontier + all-to-all rebalance; the
             # stitched tree is gathered to rank 0 inside the timed region (end-to-end)
-            res, info = partition_distributed(orc, roots, gather=True, wave=args.wave or 1024,
+            res, info = partition_distributed(o, rts, gather=True, wave=args.wave or 1024,
                                               waves_per_round=1 if args.round_ms <= 0 else 0,
                                               round_ms=args.round_ms, signal=args.round_ms <= 0,
-                                              fill_depth=args.fill, deal_depth=args.deal)
+                                              fill_depth=args.fill, deal_depth=args.deal,
+                                              max_nodes=max_nodes)
             if res is None:
                 res = type('R', (), dict(stats=info['stats'], nnodes=info['stats']['nnodes']))()
             else:
@@ -244,6 +368,8 @@ def main():
         walls.append(wall)
         results.append(res)
         xch.append(info)
+        if len(results) > 1:
+            results[-2] = type('R', (), dict(stats=results[-2].stats))()   # keep only the statistics
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -254,12 +380,12 @@ def main():
 
     res = results[-1]
     leaves = sum(r.stats['nleaves'] for r in results)
+    nfail = sum(r.stats['nfail'] for r in results)
     nn = res.stats['nnodes']
-    n, nu = 4, 1
-    d2h = nn * (5 * 4 + 1 + 8 * ((n + 1) * n + (n + 1) + (n + 1) * nu))
+    d2h = nn * wl.node_bytes()
     h2d = roots.nbytes // world
     tot = torch.tensor([float(leaves), float(sum(r.stats['nsolves'] for r in results)),
-                        float(launches)], dtype=torch.float64, device='cuda')
+                        float(launches), float(nfail)], dtype=torch.float64, device='cuda')
     mx = torch.tensor([sum(dev_ms) * 1e-3, sum(walls)], dtype=torch.float64, device='cuda')
     busy = torch.tensor([results[-1].stats['device_ms']], dtype=torch.float64, device='cuda')
     busy_all = torch.zeros(world, dtype=torch.float64, device='cuda')
@@ -273,74 +399,76 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    leaves_all, solves_all, launches_all = tot.tolist()
+    leaves_all, solves_all, launches_all, nfail_all = tot.tolist()
     dev_s, wall_s = mx.tolist()
     value = leaves_all / dev_s
     e2e = leaves_all / wall_s
 
-    # ---- roofline of the dominant kernel (k_lcss_eval: batched fp64 IPM) --------------------
+    fp64_peak, hbm_inrun, hbm_peak, hbm_src = _peaks()
     st = res.stats
-    pk = __import__('ctypes').c_double()
-    _capi.check(_capi.lib().ehm_fp64_peak(__import__('ctypes').byref(pk)))
-    hb = __import__('ctypes').c_double()
-    _capi.check(_capi.lib().ehm_hbm_peak(1 << 30, __import__('ctypes').byref(hb)))
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    hbm_peak, hbm_src = 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
-    if os.path.exists(peaks_path):
-        try:
-            hbm_peak = float(json.load(open(peaks_path))['hbm_gbs'])
-            hbm_src = 'MEASURED_PEAKS.json'
-        except Exception:
-            pass
-    stage_names = ['k_pop', 'k_lcss_ref', 'k_lcss_items', 'k_lcss_eval', 'k_lcss_select',
-                   'k_lcss_points', 'k_lcss_final', 'ecc_phase']
+    roofline = _roofline(st, fp64_peak, wl.config)
     sm = st['stage_ms']
-    dom = int(np.argmax(sm))
-    solve_ms = sm[1] + sm[3] + sm[5] + sm[7]
-    solve_fl = st['stage_flops'][1] + st['stage_flops'][3] + st['stage_flops'][5] + st['stage_flops'][7]
-    ach = st['stage_flops'][3] / (sm[3] * 1e-3) / 1e12 if sm[3] > 0 else 0.0
-    traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, 'profiles', 'r1_final_traffic.json')
-    if os.path.exists(tp):
-        try:
-            tj = json.load(open(tp))
-            traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
-        except Exception:
-            pass
-    roofline = dict(bound='fp64', kernel='k_lcss_eval (warp-per-problem IPM)', achieved=ach,
-                    peak=pk.value, unit='TFLOP/s', frac=ach / pk.value if pk.value else None,
-                    traffic=traffic, traffic_unit='dram bytes of ONE saturated launch (not per step)',
-                    traffic_source=traffic_src,
-                    note='fp64 FMA-pipe bound (SURVEY 8d): peak = in-run DFMA microbenchmark '
-                         '(ehm_fp64_peak); achieved = algorithmic flops of all k_lcss_eval launches '
-                         'of the last step / their summed CUDA-event time; all IPM kernels together: '
-                         '%.2f TFLOP/s over %.1f ms' % (solve_fl / (solve_ms * 1e-3) / 1e12, solve_ms),
-                    stage_ms={stage_names[k]: round(sm[k], 3) for k in range(8)},
-                    dominant_stage=stage_names[dom])
     pop_gbs = st['stage_bytes'][0] / (sm[0] * 1e-3) / 1e9 if sm[0] > 0 else 0.0
     roofline_hbm = dict(bound='hbm', kernel='k_pop (frontier record stream)', achieved=pop_gbs,
                         peak=hbm_peak, unit='GB/s', frac=pop_gbs / hbm_peak, traffic=None,
-                        peak_source=hbm_src, in_run_copy_gbs=hb.value)
+                        peak_source=hbm_src, in_run_copy_gbs=hbm_inrun)
 
-    cpu = None
+    parity = None
+    if wl.config == 2 and world == 1:
+        parity = _check_config2(res)
+        assert parity['leaf_sets_bit_exact'], parity
+    assert nfail_all == 0, 'numerical failures in the timed partitions: %d' % nfail_all
+
+    cpu, same_sample = None, None
     if not args.no_cpu_baseline and world == 1:
         threads = _host_cores()
-        sample = _cpu_sample(threads)
-        c = cpu_leg(threads, sample)
+        sample = wl.cpu_sample(threads)
+        c = cpu_leg(wl, threads, sample)
         cpu = dict(value=c['value'], unit='leaves/s', cores=threads, kind='port',
-                   sample='%d cheapest root simplices of the same workload (%d leaves, %.1f s)'
-                          % (len(sample), c['leaves'], c['seconds']),
-                   solves_per_s=c['solves_per_s'])
+                   sample=_sample_text(wl, sample, c), solves_per_s=c['solves_per_s'],
+                   note='CPU restatement of the reference algorithm with all of this repository\'s condensing, '
+                        'pre-solve and pruning (not MOSEK: ~10 solves/s/core, lib/post_process.py:328-330)')
+        # the GPU on exactly the sample the CPU legs partition: a same-work ratio
+        rs = partition(orc, roots[sample], wave=args.wave, max_nodes=wl.max_nodes)
+        rs2 = partition(orc, roots[sample], wave=args.wave, max_nodes=wl.max_nodes)
+        g = rs2.stats['nleaves'] / (rs2.stats['device_ms'] * 1e-3)
+        same_sample = dict(sample=[wl.root_ids[i] for i in sample], gpu_leaves=int(rs2.stats['nleaves']),
+                           cpu_leaves=int(c['leaves']), gpu_leaves_per_s=g, cpu_leaves_per_s=c['value'],
+                           gpu_ms=rs2.stats['device_ms'], cpu_s=c['seconds'], ratio=g / c['value'],
+                           same_leaf_count=bool(rs.stats['nleaves'] == c['leaves']),
+                           note='identical root simplices on both sides (the sample is too small to fill the GPU: '
+                                'the full-workload number is the headline)')
+
+    # secondary: BASELINE configs[1] (tree-equality config) in the same line of the default run
+    secondary = None
+    if wl.config == 5 and world == 1 and not args.no_secondary:
+        w2 = Workload(2)
+        o2 = Oracle(w2.mpc, w2.eps_a, w2.eps_r)
+        rr = None
+        ms2 = []
+        for i in range(2 + 2):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            rr = partition(o2, w2.roots)
+            if i >= 2:
+                ms2.append(rr.stats['device_ms'])
+        par = _check_config2(rr)
+        secondary = dict(workload=w2.name, value=rr.stats['nleaves'] / (np.mean(ms2) * 1e-3), unit='leaves/s',
+                         ms_per_step=float(np.mean(ms2)), steps=2, warmup=2, leaves_per_step=int(rr.stats['nleaves']),
+                         nfail=int(rr.stats['nfail']), parity=par,
+                         oracle_solves_per_s=rr.stats['nsolves'] / (rr.stats['device_ms'] * 1e-3),
+                         roofline=_roofline(rr.stats, fp64_peak, 2))
+        del o2, rr
 
     # secondary: online evaluation of the produced control law, not timed above
     online = None
-    if world == 1:
+    if world == 1 and wl.config in (2, 3):
         try:
             from explicit_hybrid_mpc_b200.mpc_library import ExplicitMPC
             empc = ExplicitMPC(res)
             nq = 1 << 21
-            X = (torch.rand(nq, 4, dtype=torch.float64, device='cuda') * 2 - 1) * torch.tensor(
-                mpc.theta_scale, device='cuda')
+            X = (torch.rand(nq, wl.n, dtype=torch.float64, device='cuda') * 2 - 1) * torch.tensor(
+                wl.mpc.theta_scale, device='cuda')
             empc.evaluate_batch(X[:1024])
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -361,10 +489,9 @@ def main():
         metric=METRIC, value=value, unit='leaves/s', n_gpus=world, steps=args.steps,
         warmup=args.warmup, ms_per_step=dev_s * 1e3 / args.steps, higher_is_better=True,
         scaling='strong', vs_baseline=None, dtype='f64', data='synthetic',
-        config=dict(workload='pendulum N=5 abs_frac=0.25 eps_r=1.0, 66 Delaunay root simplices '
-                             '(BASELINE.json configs[1])',
-                    eps_a=eps_a, leaves_per_step=leaves_all / args.steps,
-                    nodes_per_step=nn if world == 1 else None,
+        config=dict(workload=wl.name, survey_config=wl.config,
+                    eps_a=eps_a, eps_r=wl.eps_r, leaves_per_step=leaves_all / args.steps,
+                    nodes_per_step=nn if world == 1 else None, nfail=int(nfail_all),
                     parallelism=('single GPU' if world == 1 else 'frontier sharded over %d ranks: roots dealt '
                                  'round-robin; ranks meet (all-gather of depths) when one raises a starvation flag%s; '
                                  'NCCL all-to-all of frontier records: one interleaved shuffle after the ramp-up, '
@@ -378,7 +505,8 @@ def main():
         oracle_solves_per_s=solves_all / dev_s,
         gpu_launches=int(launches_all),
         clocks=_clocks_summary(samples),
-        roofline=roofline, roofline_hbm=roofline_hbm, cpu_baseline=cpu,
+        roofline=roofline, roofline_hbm=roofline_hbm, cpu_baseline=cpu, same_sample=same_sample,
+        parity=parity, pendulum_config2=secondary,
         online_evaluation=online,
         rank_busy_ms_last_step=[round(x, 1) for x in busy_all.tolist()],
         wall_s_timed_region=t_total)

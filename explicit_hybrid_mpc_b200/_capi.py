@@ -25,7 +25,8 @@ EXPORTS = [
     'ehm_partition_advance', 'ehm_partition_advance_for', 'ehm_locator_create', 'ehm_locator_eval',
     'ehm_locator_destroy', 'ehm_partition_export', 'ehm_partition_import',
     'ehm_partition_fetch_origin', 'ehm_partition_set_root_ids', 'ehm_last_failure',
-    'ehm_debug_trace', 'ehm_debug_fetch',
+    'ehm_debug_trace', 'ehm_debug_fetch', 'ehm_p_theta_batch', 'ehm_v_r_batch', 'ehm_bar_e_batch',
+    'ehm_bar_d_batch',
 ]
 
 
@@ -89,24 +90,28 @@ def lib():
         L.ehm_read_counters.argtypes = [vp] + [C.POINTER(C.c_int64)] * 3
         L.ehm_fp64_peak.argtypes = [C.POINTER(C.c_double)]
         L.ehm_hbm_peak.argtypes = [C.c_int64, C.POINTER(C.c_double)]
-        if hasattr(L, 'ehm_partition_run'):
-            L.ehm_partition_run.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
-                                            C.POINTER(PartitionOpts), C.POINTER(vp),
-                                            C.POINTER(PartitionStats)]
-            L.ehm_partition_fetch.argtypes = [vp] + [vp] * 9
-            L.ehm_partition_free.argtypes = [vp]
-            L.ehm_partition_create.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
-                                               C.POINTER(PartitionOpts), C.POINTER(vp)]
-            L.ehm_partition_advance.argtypes = [vp, C.c_int64, C.POINTER(PartitionStats)]
-            L.ehm_partition_advance_for.argtypes = [vp, C.c_int64, C.c_double, C.POINTER(PartitionStats)]
-            L.ehm_locator_create.argtypes = [C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_int32,
-                                             C.POINTER(C.c_void_p)]
-            L.ehm_locator_eval.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
-            L.ehm_locator_destroy.argtypes = [vp]
-            L.ehm_partition_export.argtypes = [vp, C.c_int, vp, vp, vp]
-            L.ehm_partition_import.argtypes = [vp, C.c_int, vp, vp, vp, vp]
-            L.ehm_partition_fetch_origin.argtypes = [vp, vp]
-            L.ehm_partition_set_root_ids.argtypes = [vp, C.c_int, vp]
+        L.ehm_partition_run.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
+                                        C.POINTER(PartitionOpts), C.POINTER(vp),
+                                        C.POINTER(PartitionStats)]
+        L.ehm_partition_fetch.argtypes = [vp] + [vp] * 9
+        L.ehm_partition_free.argtypes = [vp]
+        L.ehm_partition_create.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
+                                           C.POINTER(PartitionOpts), C.POINTER(vp)]
+        L.ehm_partition_advance.argtypes = [vp, C.c_int64, C.POINTER(PartitionStats)]
+        L.ehm_partition_advance_for.argtypes = [vp, C.c_int64, C.c_double, C.POINTER(PartitionStats)]
+        L.ehm_locator_create.argtypes = [C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_int32,
+                                         C.POINTER(C.c_void_p)]
+        L.ehm_locator_eval.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+        L.ehm_locator_destroy.argtypes = [vp]
+        L.ehm_partition_export.argtypes = [vp, C.c_int, vp, vp, vp]
+        L.ehm_partition_import.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        L.ehm_partition_fetch_origin.argtypes = [vp, vp]
+        L.ehm_partition_set_root_ids.argtypes = [vp, C.c_int, vp]
+        L.ehm_last_failure.argtypes = [vp, vp]
+        L.ehm_p_theta_batch.argtypes = [vp, C.c_int, dp, ip, dp, dp, ip, vp]
+        L.ehm_v_r_batch.argtypes = [vp, C.c_int, dp, ip, dp, dp, ip, vp]
+        L.ehm_bar_e_batch.argtypes = [vp, C.c_int, dp, dp, ip, dp, vp]
+        L.ehm_bar_d_batch.argtypes = [vp, C.c_int, dp, dp, ip, ip, dp, dp, dp, ip, ip, vp]
         _lib = L
     return _lib
 

@@ -46,6 +46,7 @@ struct ehm_problem {
     ehm::DevCounters *dcnt = nullptr;
     int sm_count = 148;
     void *parked = nullptr;   // one retired ehm_partition whose device buffers are reused
+    void *oscr = nullptr;     // ehm::OracleScratch of the batched oracle calls (grow-only)
     std::vector<double> u_dummy;
 };
 

@@ -73,6 +73,28 @@ __device__ __forceinline__ double warp_min_nonneg(double v)
     return __hiloint2double((int)mh, (int)ml);
 }
 
+// 1/x and 1/sqrt(x) for finite positive x: hardware seed (MUFU.RCP64H / RSQ64H, ~2^-23) + two
+// Newton steps (error below 2 ulp), branch free -- the IEEE-rounded library versions carry a slow
+// path that costs a divergence frame (BSSY/BSYNC) at every call site.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-(x * y), y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+
 // D(8x8) += A(8x4) * B(4x8), fp64 tensor path.  Fragments: a = A[lane/4][lane%4],
 // b = B[lane%4][lane/4], c0/c1 = C[lane/4][2*(lane%4) + 0/1].
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -80,6 +102,18 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+
+// Sum of one double per lane over the warp, result in every lane, with two DMMAs: the lane's
+// value is its B fragment B[lane%4][lane/4], A = ones, so D[.][j] = sum of lanes 4j..4j+3 and the
+// lane ends up with two of those; a second pass over their sum adds the four pairs.  6 SASS
+// instructions instead of the ~60 of a 5-level 64-bit shuffle tree (see chol_small).
+__device__ __forceinline__ double warp_sum_mma(double v)
+{
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    dmma884(c0, c1, 1.0, v);
+    dmma884(d0, d1, 1.0, c0 + c1);
+    return d0;
 }
 
 constexpr int tile_width(int nv)
@@ -110,32 +144,169 @@ struct IpmWs {
     static constexpr int oF = (oHs + NV * HS + 1) & ~1;        // f        (NVP)
     static constexpr int oZ = oF + NVP;                        // z in/out (NVP)
     static constexpr int oDz = oZ + NVP;                       // dz       (NVP)
-    static constexpr int oOut = oDz + NVP;                     // [0] objective [1] iterations [2] flops [3] flags
+    static constexpr int oDiag = oDz + NVP;                    // original diagonal of K (NVP)
+    static constexpr int oRed = oDiag + NVP;                   // partial sums of gt_vec (32)
+    static constexpr int oOut = oRed + 32;                     // [0] objective [1] iterations [2] flops [3] flags
     static constexpr int kDoubles = oOut + 8;
 };
 
-// acc_k = sum_{r < m} T[r][k] * T[r][col] for k < NV, returned in lane k (all lanes with the same
-// lane % GW hold the same value).  Lanes are split into 32/GW groups that take rows round-robin.
+// acc_k = sum_{r < m} T[r][k] * T[r][col] for k < NV, returned in lane k.  The lanes form
+// 32/NV groups of NV lanes that take the rows round-robin; the partial sums meet by shuffle.
 template <int NV, int CAP>
-__device__ __forceinline__ double gt_vec(const double *__restrict__ T, int col, int m, int lane)
+__device__ __forceinline__ double gt_vec(const double *__restrict__ T, double *red, int col, int m, int lane)
 {
     using W = IpmWs<NV, CAP>;
-    constexpr int GW = NV <= 8 ? 8 : (NV <= 16 ? 16 : 32), NG = 32 / GW;
-    const int k = lane % GW, g = lane / GW;
+    constexpr int NG = 32 / NV;
+    const int g = lane / NV, k = lane - g * NV;
     double acc = 0.0, acc2 = 0.0;
-    if (k < NV) {
+    if (g < NG) {
+        const double *p = T + g * W::TW;
         int r = g;
 #pragma unroll 2
-        for (; r + NG < m; r += 2 * NG) {
-            acc = fma(T[r * W::TW + k], T[r * W::TW + col], acc);
-            acc2 = fma(T[(r + NG) * W::TW + k], T[(r + NG) * W::TW + col], acc2);
+        for (; r + NG < m; r += 2 * NG, p += 2 * NG * W::TW) {
+            acc = fma(p[k], p[col], acc);
+            acc2 = fma(p[NG * W::TW + k], p[NG * W::TW + col], acc2);
         }
-        if (r < m) acc = fma(T[r * W::TW + k], T[r * W::TW + col], acc);
+        if (r < m) acc = fma(p[k], p[col], acc);
     }
     acc += acc2;
+    if constexpr (NG > 1) {   // partial sums of the groups meet in shared memory (no shuffles, see chol_small)
+        if (g > 0 && g < NG) red[(g - 1) * NV + k] = acc;
+        __syncwarp();
+        if (lane < NV) {
 #pragma unroll
-    for (int o = GW; o < 32; o <<= 1) acc += __shfl_xor_sync(kFull, acc, o);
+            for (int q = 0; q < NG - 1; ++q) acc += red[q * NV + lane];
+        }
+        __syncwarp();
+    }
     return acc;
+}
+
+// ---- cooperative Cholesky / triangular solves: lane i owns row i of the factor ----------------
+// Small systems (NV <= 12): every loop is unrolled at compile time, the lane's own row lives in
+// registers, row j reaches the other lanes by broadcast loads from shared memory and the pivot by
+// one shuffle.  `diag` holds the original diagonal of K (the guard compares against it).
+template <int NV, int LS>
+__device__ __forceinline__ bool chol_small(double *Ks, const double *diag, int lane, double (&Lr)[NV], double &myinv)
+{
+    // No shuffles: on sm_100a every __shfl_sync / __reduce_*_sync is wrapped in a WARPSYNC ...
+    // ENDCOLLECTIVE frame (~12 SASS instructions per 64-bit value).  The pivot of column j is
+    // recomputed by every lane from the broadcast loads of row j it needs anyway.
+    const int li = lane < NV ? lane : 0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) Lr[k] = Ks[li * LS + k];
+    double chk = 0.0;
+    myinv = 1.0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const double d0 = diag[j];
+        double v = Lr[j], d = d0, v2 = 0.0, d2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < j; ++k) {
+            const double ljk = Ks[j * LS + k];
+            if (k & 1) {
+                v2 = fma(-Lr[k], ljk, v2);
+                d2 = fma(-ljk, ljk, d2);
+            } else {
+                v = fma(-Lr[k], ljk, v);
+                d = fma(-ljk, ljk, d);
+            }
+        }
+        v += v2;
+        d += d2;
+        chk += d;                                          // NaN / Inf of any pivot surfaces here
+        d = (d <= 1e-13 * d0 || d0 <= 0.0) ? 1e100 : d;   // pivot guard (oracle: cholesky)
+        const double iv = fast_rsqrt(d);
+        if (lane == j) {
+            v = d;
+            myinv = iv;
+        }
+        Lr[j] = v * iv;
+        if (lane >= j && lane < NV) Ks[lane * LS + j] = Lr[j];
+        __syncwarp();
+    }
+    return !isfinite(chk);
+}
+
+// b_i in lane i on entry, x_i = (K^-1 b)_i in lane i on return (lanes >= NV: 0).  The solution
+// components travel through the scratch vector sb (shared memory, NV doubles); a variant in which
+// every lane runs the whole substitution redundantly (no round trips) needs 40 more registers
+// and spilled at the 128 of this kernel: 1.6x slower.
+template <int NV, int LS>
+__device__ __forceinline__ double trisolve_small(const double *Ks, double *sb, int lane, const double (&Lr)[NV],
+                                                 double myinv, double b)
+{
+    const double *col = Ks + (lane < NV ? lane : 0);
+    if (lane >= NV) b = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {   // forward  L y = b: lanes i > k update b_i with y_k
+        if (lane == k) sb[k] = b * myinv;
+        __syncwarp();
+        const double yk = sb[k];
+        if (lane > k) b = fma(-Lr[k], yk, b);
+    }
+    b *= myinv;                       // lane k was last touched at step k-1: this is y_k
+    __syncwarp();
+#pragma unroll
+    for (int i = NV - 1; i >= 0; --i) {   // backward  L' x = y: lanes k < i subtract L[i][k] x_i
+        if (lane == i) sb[i] = b * myinv;
+        __syncwarp();
+        const double xi = sb[i];
+        if (lane < i) b = fma(-col[i * LS], xi, b);
+    }
+    return lane < NV ? sb[lane < NV ? lane : 0] : 0.0;
+}
+
+// Larger systems: rolled loops, the factor stays in shared memory.
+template <int NV, int LS>
+__device__ __forceinline__ bool chol_rolled(double *Ks, const double *diag, int lane, double &myinv)
+{
+    const double *rowi = Ks + (lane < NV ? lane : 0) * LS;
+    bool bad = false;
+    myinv = 1.0;
+#pragma unroll 1
+    for (int j = 0; j < NV; ++j) {
+        const double *rowj = Ks + j * LS;
+        double v = rowi[j], v2 = 0.0;
+        int k = 0;
+#pragma unroll 4
+        for (; k + 1 < j; k += 2) {
+            v = fma(-rowi[k], rowj[k], v);
+            v2 = fma(-rowi[k + 1], rowj[k + 1], v2);
+        }
+        if (k < j) v = fma(-rowi[k], rowj[k], v);
+        v += v2;
+        double d = __shfl_sync(kFull, v, j);
+        const double d0 = diag[j];
+        bad = bad || !isfinite(d);
+        d = (d <= 1e-13 * d0 || d0 <= 0.0) ? 1e100 : d;
+        const double iv = fast_rsqrt(d);
+        if (lane >= j && lane < NV) Ks[lane * LS + j] = (lane == j) ? d * iv : v * iv;
+        myinv = (lane == j) ? iv : myinv;
+        __syncwarp();
+    }
+    return bad;
+}
+
+template <int NV, int LS>
+__device__ __forceinline__ double trisolve_rolled(const double *Ks, int lane, double myinv, double b)
+{
+    const double *rowi = Ks + (lane < NV ? lane : 0) * LS;
+    const double *col = Ks + (lane < NV ? lane : 0);
+    if (lane >= NV) b = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < NV; ++k) {
+        const double yk = __shfl_sync(kFull, b * myinv, k);
+        if (lane > k) b = fma(-rowi[k], yk, b);
+    }
+    b *= myinv;
+#pragma unroll 4
+    for (int i = NV - 1; i >= 0; --i) {
+        const double xi = __shfl_sync(kFull, b * myinv, i);
+        if (lane < i) b = fma(-col[i * LS], xi, b);
+    }
+    b *= myinv;
+    return lane < NV ? b : 0.0;
 }
 
 // Solve  min 0.5 z'Hz + f'z  s.t.  G z <= h  with one warp.  `w` = base of an IpmWs block: the
@@ -160,7 +331,7 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
     const double *__restrict__ Hs = w + W::oHs;
     const double *__restrict__ fs = w + W::oF;
     // per-row state in registers
-    double s[MR], lam[MR], hh[MR], rp[MR], rs[MR], dsdl[MR];
+    double s[MR], lam[MR], rp[MR], rs[MR], dsdl[MR];
     const double fk = lane < NV ? fs[lane] : 0.0;
     const double fmx = warp_max_nonneg(fabs(fk));
     double zk = lane < NV ? zs[lane] : 0.0;   // lane k owns z_k
@@ -170,7 +341,7 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
 #pragma unroll
     for (int j = 0; j < MR; ++j) {
         const int r = lane + 32 * j;
-        s[j] = 1.0; lam[j] = 0.0; hh[j] = 1.0; rp[j] = 0.0; rs[j] = 1.0; dsdl[j] = 0.0;
+        s[j] = 1.0; lam[j] = 0.0; rp[j] = 0.0; rs[j] = 1.0; dsdl[j] = 0.0;
         if (r < m) {
             double gz = 0.0;
 #pragma unroll
@@ -180,8 +351,7 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
                 gz = fma(g.x, zz.x, fma(g.y, zz.y, gz));
             }
             if (NV & 1) gz = fma(T[r * TW + NV - 1], zs[NV - 1], gz);
-            hh[j] = T[r * TW + W::cH];
-            s[j] = fmax(hh[j] - gz, 1.0);
+            s[j] = fmax(T[r * TW + W::cH] - gz, 1.0);
             lam[j] = 1.0 / s[j];
             T[r * TW + W::cV] = lam[j];
         }
@@ -190,7 +360,7 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
     // initial dual residual rd0 = |H z0 + f + G' lam0|
     double rd0;
     {
-        double v = gt_vec<NV, CAP>(T, W::cV, m, lane);
+        double v = gt_vec<NV, CAP>(T, w + W::oRed, W::cV, m, lane);
         if (lane < NV) {
             v += fk;
             if (hasH)
@@ -236,8 +406,8 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
                 if (32 * j < m && r < 4 * ngroups) {
                     double a = 0.0, wt = 0.0;
                     if (r < m) {
-                        rp[j] = gz[j] + s[j] - hh[j];
-                        rs[j] = __drcp_rn(s[j]);
+                        rp[j] = gz[j] + s[j] - T[r * TW + W::cH];
+                        rs[j] = fast_rcp(s[j]);
                         wt = lam[j] * rs[j];
                         a = wt * rp[j];
                         rpm = fmax(rpm, fabs(rp[j]));
@@ -257,21 +427,24 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
         }
         rpm = warp_max_nonneg(rpm);
         lmx = warp_max_nonneg(lmx);
-        mu = warp_sum(mu);
+        mu = warp_sum_mma(mu);
         // (H z + f)_k in lane k, objective, |z|
         double hzf = fk;
         if (hasH && lane < NV) {
 #pragma unroll 4
             for (int q = 0; q < NV; ++q) hzf = fma(Hs[lane * W::HS + q], zs[q], hzf);
         }
-        obj = warp_sum(lane < NV ? zk * 0.5 * (hzf + fk) : 0.0);
-        const double zm = warp_max_nonneg(fabs(zk));
-        if (!isfinite(mu) || !isfinite(rpm) || !isfinite(obj)) {
+        const double zm = warp_max_nonneg(lane < NV ? fabs(zk) : 0.0);
+        if (!isfinite(mu) || !isfinite(rpm) || !isfinite(zm)) {
             status = 2;
             break;
         }
-        const bool conv = rpm <= EHM_TOL_IPM * (1.0 + zm) && rho * rd0 <= EHM_TOL_IPM * (1.0 + fmx + lmx) &&
-                          mu <= EHM_TOL_IPM * (1.0 + fabs(obj));
+        // the objective is only needed once the residual tests pass (and on exit)
+        bool conv = rpm <= EHM_TOL_IPM * (1.0 + zm) && rho * rd0 <= EHM_TOL_IPM * (1.0 + fmx + lmx);
+        if (conv || it == EHM_MAX_ITER || g_trace_on) {
+            obj = warp_sum_mma(lane < NV ? zk * 0.5 * (hzf + fk) : 0.0);
+            conv = conv && mu <= EHM_TOL_IPM * (1.0 + fabs(obj));
+        }
         if (g_trace_on && lane == 0 && it < 120) {
             g_trace[8 * it + 0] = it; g_trace[8 * it + 1] = rpm; g_trace[8 * it + 2] = mu;
             g_trace[8 * it + 3] = obj; g_trace[8 * it + 4] = rho * rd0; g_trace[8 * it + 5] = lmx;
@@ -286,7 +459,7 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
                 if (r < m) T[r * TW + W::cV] = lam[j];
             }
             __syncwarp();
-            double v = gt_vec<NV, CAP>(T, W::cV, m, lane);
+            double v = gt_vec<NV, CAP>(T, w + W::oRed, W::cV, m, lane);
             v = lane < NV ? fabs(v + hzf) : 0.0;
             const double rdm = warp_max_nonneg(v);
             if (rdm <= EHM_TOL_RD * (1.0 + fmx + lmx)) {
@@ -336,39 +509,21 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
                         double *q = Ks + (8 * a + cr) * LS + 8 * b + cc;
                         q[0] = c[a][b][0];
                         q[1] = c[a][b][1];
+                        if (a == b) {   // the diagonal, kept aside for the pivot guard
+                            if (cr == cc) w[W::oDiag + 8 * a + cr] = c[a][b][0];
+                            if (cr == cc + 1) w[W::oDiag + 8 * a + cr] = c[a][b][1];
+                        }
                     }
         }
         __syncwarp();
         const double ak = lane < NV ? Ks[W::cA * LS + lane] : 0.0;   // (G'(w rp))_k
         // ---- Cholesky, lane i = row i, left-looking, in place ------------------------------------
-        double myinv = 1.0;
-        bool bad = false;
-        {
-            const double *rowi = Ks + (lane < NV ? lane : 0) * LS;
-#pragma unroll 1
-            for (int j = 0; j < NV; ++j) {
-                const double *rowj = Ks + j * LS;
-                const double d0 = rowj[j];
-                double v = rowi[j];
-                double v2 = 0.0;
-                int k = 0;
-#pragma unroll 2
-                for (; k + 1 < j; k += 2) {
-                    v = fma(-rowi[k], rowj[k], v);
-                    v2 = fma(-rowi[k + 1], rowj[k + 1], v2);
-                }
-                if (k < j) v = fma(-rowi[k], rowj[k], v);
-                v += v2;
-                double d = __shfl_sync(kFull, v, j);
-                if (!isfinite(d)) bad = true;
-                if (d <= 1e-13 * d0 || d0 <= 0.0) d = 1e100;   // pivot guard (oracle: cholesky)
-                const double iv = rsqrt(d);
-                __syncwarp();
-                if (lane >= j && lane < NV) Ks[lane * LS + j] = (lane == j) ? d * iv : v * iv;
-                if (lane == j) myinv = iv;
-                __syncwarp();
-            }
-        }
+        constexpr bool kSmall = NV <= 12;
+        double Lr[kSmall ? NV : 1];
+        double myinv;
+        bool bad;
+        if constexpr (kSmall) bad = chol_small<NV, LS>(Ks, w + W::oDiag, lane, Lr, myinv);
+        else bad = chol_rolled<NV, LS>(Ks, w + W::oDiag, lane, myinv);
         if (bad) {
             status = 2;
             break;
@@ -389,32 +544,20 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
                     if (r < m) T[r * TW + W::cV] = fma(sig, lam[j], (dsdl[j] - smu) * rs[j]);
                 }
                 __syncwarp();
-                const double c1 = gt_vec<NV, CAP>(T, W::cV, m, lane);
+                const double c1 = gt_vec<NV, CAP>(T, w + W::oRed, W::cV, m, lane);
                 b = fma(-cres, hzf + ak, c1);
             }
             if (lane >= NV) b = 0.0;
-            // forward  L y = b  (column oriented: y_k travels by shuffle, lane i updates b_i)
-            {
-                const double *rowi = Ks + (lane < NV ? lane : 0) * LS;
-#pragma unroll 1
-                for (int k = 0; k < NV; ++k) {
-                    const double yk = __shfl_sync(kFull, b * myinv, k);
-                    if (lane == k) b = yk;
-                    else if (lane > k && lane < NV) b = fma(-rowi[k], yk, b);
-                }
-                // backward  L' x = y:  x_i final in lane i, lanes k < i subtract L[i][k] x_i
-#pragma unroll 1
-                for (int i = NV - 1; i >= 0; --i) {
-                    const double xi = __shfl_sync(kFull, b * myinv, i);
-                    if (lane == i) b = xi;
-                    else if (lane < i) b = fma(-Ks[i * LS + lane], xi, b);
-                }
-            }
+                        if constexpr (kSmall) b = trisolve_small<NV, LS>(Ks, dzs, lane, Lr, myinv, b);
+            else b = trisolve_rolled<NV, LS>(Ks, lane, myinv, b);
             dzk = b;
-            if (lane < W::NVP) dzs[lane] = lane < NV ? b : 0.0;
+            if (lane < W::NVP) dzs[lane] = b;
             __syncwarp();
-            // step to the boundary: min over rows of s/(-ds) and lam/(-dl), as fractions
-            double an = 1e300, ad = 1.0;
+            // step to the boundary: min over rows of s/(-ds) and lam/(-dl).  The ratios are formed
+            // in fp32 (the step only has to stay inside the cone: it is scaled by 0.99 below, which
+            // dwarfs the 1e-7 of fp32, and the predictor's length merely sets sigma), which lets one
+            // 32-bit REDUX find the minimum.
+            float amin = 3.0e38f;
             {
                 double gd[MR];
 #pragma unroll
@@ -447,8 +590,10 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
                         const double rc = trip ? fma(s[j], lam[j], dsdl[j] - smu) : s[j] * lam[j];
                         const double ds = -cres * rp[j] - gd[j];
                         const double dl = (-rc - lam[j] * ds) * rs[j];
-                        if (ds < 0.0 && s[j] * ad < an * (-ds)) { an = s[j]; ad = -ds; }
-                        if (dl < 0.0 && lam[j] * ad < an * (-dl)) { an = lam[j]; ad = -dl; }
+                        // s / (-ds) where ds < 0 (else +inf), fp32 with the hardware reciprocal (1 ulp)
+                        const float qs = __double2float_rz(s[j]) * __frcp_rn(__double2float_ru(fmax(-ds, 0.0)));
+                        const float ql = __double2float_rz(lam[j]) * __frcp_rn(__double2float_ru(fmax(-dl, 0.0)));
+                        amin = fminf(amin, fminf(qs, ql));
                         if (trip) {
                             rp[j] = ds;     // rp / dsdl are dead from here on: they carry the step
                             dsdl[j] = dl;
@@ -458,7 +603,7 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, boo
                     }
                 }
             }
-            const double amax = warp_min_nonneg(an / ad);
+            const double amax = (double)__uint_as_float(__reduce_min_sync(kFull, __float_as_uint(amin)));
             if (trip == 0) {
                 const double a_aff = fmin(1.0, amax);
                 sig = (1.0 - a_aff) * (1.0 - a_aff) * (1.0 - a_aff);

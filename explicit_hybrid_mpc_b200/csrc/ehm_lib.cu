@@ -19,8 +19,11 @@ using namespace ehm;
 // (stage rows that survive the pre-solve + n+1 simplex rows + two epigraph rows), WPC warps
 // (= problems) per CTA, CPS CTAs per SM (shared memory per problem: WarpWs<U,NX,CAP>)
 // ---------------------------------------------------------------------------------------
+#ifndef EHM_CPS_PEND
+#define EHM_CPS_PEND 4
+#endif
 #define EHM_FOR_EACH_CFG(X)                                                                      \
-    X(0, 5, 4, 80, 4, 4)  /* inverted pendulum, N=5: 217 rows in, 41-68 after the pre-solve   */ \
+    X(0, 5, 4, 80, 4, EHM_CPS_PEND)  /* inverted pendulum, N=5: 217 rows in, 41-68 after the pre-solve   */ \
     X(1, 2, 2, 32, 4, 4)  /* two-mode toy problem of the ECC-split test (tests/golden)        */ \
     X(2, 16, 8, 96, 1, 5) /* synthetic n=8 mp-LP: 91 rows, NV = 25       */
 
@@ -40,6 +43,7 @@ static int find_cfg(int U, int NX)
 }
 
 static void ehm_partition_free_now(void *t);   // defined with ehm_partition below
+static void ehm_oracle_scratch_free(void *s); // defined with the batched oracle calls below
 
 __device__ __forceinline__ long long next_item(DevCounters *cnt, int lane)
 {
@@ -319,6 +323,7 @@ extern "C" int ehm_problem_destroy(ehm_problem *p)
     }
     cudaFree(p->dG); cudaFree(p->dS); cudaFree(p->dg); cudaFree(p->drho); cudaFree(p->dM);
     cudaFree(p->dcnt);
+    ehm_oracle_scratch_free(p->oscr);
     delete p;
     return EHM_OK;
 }
@@ -436,6 +441,7 @@ extern "C" int ehm_read_counters(ehm_problem *p, int64_t *iters, int64_t *solves
 // =========================================================================================
 #include "ehm_partition.cuh"
 #include "ehm_locate.cuh"
+#include "ehm_oracle_batch.cuh"
 
 struct ehm_partition {
     ehm_problem *pb = nullptr;
@@ -528,9 +534,9 @@ int advance_t(ehm_partition *t, int64_t max_waves, double budget_ms)
         const int ne = std::min(kEccWave, h.necc_next - q0);
         EHM_CUDA(cudaEventRecord(sev[0], st));
         k_reset_cursors<<<1, 32, 0, st>>>(t->dctl);
-        kecc<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->eb, q0, ne, 0, t->dctl, p->dcnt);
+        kecc<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->eb, q0, ne, 0, t->dctl, p->dcnt, nullptr);
         k_ecc_pick<NX><<<(ne * 32 + 127) / 128, 128, 0, st>>>(tb, t->eb, ne, t->dctl);
-        kecc<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->eb, q0, ne, 1, t->dctl, p->dcnt);
+        kecc<<<gsolve, tsolve, smem, st>>>(tb, t->ns, t->eb, q0, ne, 1, t->dctl, p->dcnt, nullptr);
         k_ecc_final<NX><<<(ne * 32 + 127) / 128, 128, 0, st>>>(tb, t->ns, t->fr, t->eb, q0, ne, t->dctl);
         EHM_CUDA(cudaEventRecord(sev[1], st));
         launches += 5;
@@ -866,6 +872,189 @@ extern "C" int ehm_partition_free(ehm_partition *t)
 }
 
 // =========================================================================================
+// batched reference-shaped oracle calls (kernels in ehm_oracle_batch.cuh)
+// =========================================================================================
+namespace {
+
+int oracle_scratch(ehm_problem *p, int B, OracleScratch **out)
+{
+    OracleScratch *sc = (OracleScratch *)p->oscr;
+    if (sc && sc->cap >= B) { *out = sc; return EHM_OK; }
+    delete sc;
+    p->oscr = nullptr;
+    sc = new OracleScratch();
+    const int cap = std::max(B, 8);
+    const DevTables &tb = p->tb;
+    const size_t n = tb.n, nu = tb.nu, nc = tb.ncand, W = cap, WN = W * nc;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](auto **ptr, size_t count) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc((void **)ptr, std::max<size_t>(count, 1) * sizeof(**ptr));
+        if (e == cudaSuccess) sc->allocs.push_back((void *)*ptr);
+    };
+    WaveBuf &wv = sc->wv;
+    EccBuf &eb = sc->eb;
+    wv.W = cap;
+    A(&wv.node, W); A(&wv.skip, W); A(&wv.lb, WN); A(&wv.tref, W); A(&wv.tval, WN); A(&wv.titem, WN);
+    A(&wv.items, WN); A(&wv.it_sol, WN * (n + 1)); A(&wv.it_pl, WN * (n + 1)); A(&wv.sel, W * kSelT);
+    A(&wv.nsel, W); A(&wv.nimp, W); A(&wv.conv, W); A(&wv.ij, 2 * W); A(&wv.vmid, W * n);
+    A(&wv.pitems, W * ((kSelT + 1) * (n + 2) + 1)); A(&wv.ptJ, W * (kSelT + 1) * (n + 2));
+    A(&wv.ptU, W * (kSelT + 1) * (n + 2) * nu); A(&wv.ptS, W * (kSelT + 1) * (n + 2));
+    A(&wv.minv, W); A(&wv.minv_st, W);
+    A(&eb.queue, W); A(&eb.J, WN * (n + 2)); A(&eb.U, WN * (n + 1) * nu); A(&eb.S, WN * (n + 2)); A(&eb.pick, W);
+    A(&sc->dctl, 1); A(&sc->more, 1); A(&sc->neg1, W);
+    if (e != cudaSuccess) {
+        delete sc;
+        return fail(EHM_ENOMEM, std::string("oracle scratch: ") + cudaGetErrorString(e));
+    }
+    sc->cap = cap;
+    p->oscr = sc;
+    *out = sc;
+    return EHM_OK;
+}
+
+// the caller's arrays viewed as a node store: entry e = node e
+NodeStore view_of(int B, const double *R, const double *Vr, const int *cref)
+{
+    NodeStore ns{};
+    ns.cap = B;
+    ns.verts = const_cast<double *>(R);
+    ns.vcost = const_cast<double *>(Vr);
+    ns.cand = const_cast<int *>(cref);
+    return ns;
+}
+
+template <class SH>
+int pick_t(ehm_problem *p, OracleScratch *sc, int B, const double *d_R, const double *d_theta, int nslots,
+           int *d_cand, double *d_J, double *d_U, int *d_status, cudaStream_t st)
+{
+    constexpr int NX = SH::NX;
+    auto kecc = k_ecc_points<SH>;
+    int rc = set_smem(kecc, SH::smem);
+    if (rc) return rc;
+    const NodeStore ns = view_of(B, d_R, nullptr, nullptr);
+    const int gaux = p->sm_count * 4;
+    k_batch_init<<<gaux, 256, 0, st>>>(sc->wv, sc->eb, B, p->tb.ncand, sc->dctl, sc->more, sc->neg1);
+    kecc<<<p->sm_count * SH::CPS, 32 * SH::WPC, SH::smem, st>>>(p->tb, ns, sc->eb, 0, B, d_theta ? 2 : 0, sc->dctl,
+                                                                 p->dcnt, d_theta);
+    k_ecc_pick<NX><<<(B * 32 + 127) / 128, 128, 0, st>>>(p->tb, sc->eb, B, sc->dctl, nslots);
+    k_batch_pick_out<NX><<<(B + 127) / 128, 128, 0, st>>>(p->tb, sc->eb, B, nslots, d_cand, d_J, d_U, d_status);
+    g_launches += 4;
+    EHM_CUDA(cudaGetLastError());
+    return EHM_OK;
+}
+
+template <class SH>
+int bar_t(ehm_problem *p, OracleScratch *sc, int B, const double *d_R, const double *d_Vr, const int *d_cref,
+          int *d_conv, double *d_tmin, int *d_cstar, double *d_theta, double *d_Jv, double *d_Uv, int *d_vs,
+          int *d_status, cudaStream_t st)
+{
+    constexpr int NX = SH::NX;
+    auto kref = k_lcss_ref<SH>;
+    auto keval = k_lcss_eval<SH>;
+    auto kpts = k_lcss_points<SH>;
+    int rc;
+    if ((rc = set_smem(kref, SH::smem)) || (rc = set_smem(keval, SH::smem)) || (rc = set_smem(kpts, SH::smem))) return rc;
+    const DevTables &tb = p->tb;
+    const NodeStore ns = view_of(B, d_R, d_Vr, d_cref ? d_cref : sc->neg1);
+    const int gaux = p->sm_count * 4, gsolve = p->sm_count * SH::CPS, tsolve = 32 * SH::WPC;
+    k_batch_init<<<gaux, 256, 0, st>>>(sc->wv, sc->eb, B, tb.ncand, sc->dctl, sc->more, sc->neg1);
+    if (d_cref) kref<<<gsolve, tsolve, SH::smem, st>>>(tb, ns, sc->wv, B, sc->dctl, p->dcnt);
+    k_lcss_items<<<gaux, 256, 0, st>>>(ns, sc->wv, B, tb.ncand, sc->dctl);
+    keval<<<gsolve, tsolve, SH::smem, st>>>(tb, ns, sc->wv, sc->dctl, p->dcnt);
+    g_launches += 3 + (d_cref ? 1 : 0);
+    if (!d_cstar) {   // bar_E
+        k_lcss_select<NX><<<gaux, 256, 0, st>>>(ns, sc->wv, B, tb.ncand, sc->dctl);
+        k_batch_bare_out<<<(B * 32 + 127) / 128, 128, 0, st>>>(sc->wv, B, tb.ncand, d_conv, d_tmin);
+        g_launches += 2;
+        EHM_CUDA(cudaGetLastError());
+        return EHM_OK;
+    }
+    for (int round = 0; round < 1 + tb.ncand / kSelT; ++round) {   // bar_D: vet kSelT candidates per round
+        k_batch_round<<<1, 32, 0, st>>>(sc->dctl, sc->more);
+        k_lcss_select<NX><<<gaux, 256, 0, st>>>(ns, sc->wv, B, tb.ncand, sc->dctl);
+        kpts<<<gsolve, tsolve, SH::smem, st>>>(tb, ns, sc->wv, sc->dctl, p->dcnt);
+        k_batch_bard_out<NX><<<(B + 127) / 128, 128, 0, st>>>(tb, ns, sc->wv, B, d_cstar, d_theta, d_Jv, d_Uv, d_vs,
+                                                             d_status, sc->more);
+        g_launches += 4;
+        int more = 0;
+        EHM_CUDA(cudaMemcpyAsync(&more, sc->more, sizeof(int), cudaMemcpyDeviceToHost, st));
+        EHM_CUDA(cudaStreamSynchronize(st));
+        if (more == 0) break;
+    }
+    EHM_CUDA(cudaGetLastError());
+    return EHM_OK;
+}
+
+}  // namespace
+
+static void ehm_oracle_scratch_free(void *s) { delete (ehm::OracleScratch *)s; }
+
+#define EHM_DISPATCH(CALL)                                               \
+    switch (p->cfg) {                                                    \
+        EHM_FOR_EACH_CFG(X)                                              \
+    default: return fail(EHM_EINVAL, "no kernel for this problem shape"); \
+    }
+
+extern "C" int ehm_p_theta_batch(ehm_problem *p, int B, const double *d_theta, int *d_cand, double *d_J,
+                                 double *d_u0, int *d_status, void *stream)
+{
+    if (!p || B < 0 || !d_theta || !d_cand) return fail(EHM_EINVAL, "bad argument");
+    if (B == 0) return EHM_OK;
+    OracleScratch *sc;
+    int rc = oracle_scratch(p, B, &sc);
+    if (rc) return rc;
+#define X(ID, UU, NN, CC, WW, PP) \
+    case ID: return pick_t<Shape<UU, NN, CC, WW, PP>>(p, sc, B, nullptr, d_theta, 1, d_cand, d_J, d_u0, d_status, (cudaStream_t)stream);
+    EHM_DISPATCH(X)
+#undef X
+}
+
+extern "C" int ehm_v_r_batch(ehm_problem *p, int B, const double *d_R, int *d_cand, double *d_Jv, double *d_Uv,
+                             int *d_status, void *stream)
+{
+    if (!p || B < 0 || !d_R || !d_cand) return fail(EHM_EINVAL, "bad argument");
+    if (B == 0) return EHM_OK;
+    OracleScratch *sc;
+    int rc = oracle_scratch(p, B, &sc);
+    if (rc) return rc;
+#define X(ID, UU, NN, CC, WW, PP) \
+    case ID: return pick_t<Shape<UU, NN, CC, WW, PP>>(p, sc, B, d_R, nullptr, NN + 1, d_cand, d_Jv, d_Uv, d_status, (cudaStream_t)stream);
+    EHM_DISPATCH(X)
+#undef X
+}
+
+extern "C" int ehm_bar_e_batch(ehm_problem *p, int B, const double *d_R, const double *d_Vr, int *d_converged,
+                               double *d_tmin, void *stream)
+{
+    if (!p || B < 0 || !d_R || !d_Vr || !d_converged) return fail(EHM_EINVAL, "bad argument");
+    if (B == 0) return EHM_OK;
+    OracleScratch *sc;
+    int rc = oracle_scratch(p, B, &sc);
+    if (rc) return rc;
+#define X(ID, UU, NN, CC, WW, PP) \
+    case ID: return bar_t<Shape<UU, NN, CC, WW, PP>>(p, sc, B, d_R, d_Vr, nullptr, d_converged, d_tmin, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    EHM_DISPATCH(X)
+#undef X
+}
+
+extern "C" int ehm_bar_d_batch(ehm_problem *p, int B, const double *d_R, const double *d_Vr, const int *d_cand_ref,
+                               int *d_cand_star, double *d_theta_star, double *d_Jv, double *d_Uv,
+                               int *d_var_small, int *d_status, void *stream)
+{
+    if (!p || B < 0 || !d_R || !d_Vr || !d_cand_ref || !d_cand_star || !d_theta_star || !d_Jv || !d_Uv || !d_var_small)
+        return fail(EHM_EINVAL, "bad argument");
+    if (B == 0) return EHM_OK;
+    OracleScratch *sc;
+    int rc = oracle_scratch(p, B, &sc);
+    if (rc) return rc;
+#define X(ID, UU, NN, CC, WW, PP) \
+    case ID: return bar_t<Shape<UU, NN, CC, WW, PP>>(p, sc, B, d_R, d_Vr, d_cand_ref, nullptr, nullptr, d_cand_star, d_theta_star, d_Jv, d_Uv, d_var_small, d_status, (cudaStream_t)stream);
+    EHM_DISPATCH(X)
+#undef X
+}
+
+// =========================================================================================
 // measurement helpers
 // =========================================================================================
 __global__ void k_dfma_peak(double *out, int iters)
@@ -1018,8 +1207,9 @@ extern "C" int ehm_locator_create(int n, int nu, int64_t nnodes, const int32_t *
 }
 
 extern "C" int ehm_locator_eval(ehm_locator *l, int64_t B, const double *d_theta, double *d_u, int32_t *d_leaf,
-                                cudaStream_t stream)
+                                void *stream_)
 {
+    cudaStream_t stream = (cudaStream_t)stream_;
     if (!l || B < 0 || (B > 0 && (!d_theta || !d_u))) return fail(EHM_EINVAL, "bad argument");
     if (B == 0) return EHM_OK;
     const unsigned grid = (unsigned)((B + 127) / 128);

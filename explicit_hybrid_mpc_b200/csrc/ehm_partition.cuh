@@ -587,8 +587,11 @@ __global__ void k_lcss_final(DevTables tb, NodeStore ns, Frontier fr, WaveBuf wv
 // ------------------------------------------------------------------------------------------
 template <class SH>
 __global__ void __launch_bounds__(32 * SH::WPC, SH::CPS)
-k_ecc_points(DevTables tb, NodeStore ns, EccBuf eb, int q0, int ne, int centroid, Ctl *ctl, DevCounters *cnt)
+k_ecc_points(DevTables tb, NodeStore ns, EccBuf eb, int q0, int ne, int centroid, Ctl *ctl, DevCounters *cnt,
+             const double *__restrict__ theta = nullptr)
 {
+    // centroid: 0 = the n+1 vertices of every entry (V_R), 1 = the barycentre of the entries without
+    // a common commutation (worker.py:264-266), 2 = the explicit point theta[e] (P_theta batch)
     extern __shared__ __align__(16) double smem[];
     constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -597,17 +600,19 @@ k_ecc_points(DevTables tb, NodeStore ns, EccBuf eb, int q0, int ne, int centroid
     const long long per = centroid ? ncand : (long long)ncand * (NX + 1);
     const long long total = per * ne;
     for (;;) {
-        const long long q = grab(&ctl->cur[centroid ? 4 : 3], lane);
+        const long long q = grab(&ctl->cur[centroid == 1 ? 4 : 3], lane);
         if (q >= total) break;
         const int e = (int)(q / per);
         const long long r = q % per;
         const int c = centroid ? (int)r : (int)(r / (NX + 1));
-        const int i = centroid ? NX + 1 : (int)(r % (NX + 1));
-        const int nd = eb.queue[q0 + e];
-        if (centroid && eb.pick[e] != -1) continue;  // only entries without a common delta
+        const int i = centroid == 2 ? 0 : (centroid ? NX + 1 : (int)(r % (NX + 1)));
+        const int nd = centroid == 2 ? 0 : eb.queue[q0 + e];
+        if (centroid == 1 && eb.pick[e] != -1) continue;  // only entries without a common delta
         double th[NX];
         const double *R = ns.verts + (size_t)nd * (NX + 1) * NX;
-        if (centroid) {
+        if (centroid == 2) {
+            for (int k = 0; k < NX; ++k) th[k] = theta[(size_t)e * NX + k];
+        } else if (centroid) {
             for (int k = 0; k < NX; ++k) {
                 double acc = 0.0;
                 for (int v = 0; v <= NX; ++v) acc += R[v * NX + k];
@@ -636,8 +641,9 @@ k_ecc_points(DevTables tb, NodeStore ns, EccBuf eb, int q0, int ne, int centroid
 
 // per ECC entry: canonical V_R choice (one warp per entry)
 template <int NX>
-__global__ void k_ecc_pick(DevTables tb, EccBuf eb, int ne, Ctl *ctl)
+__global__ void k_ecc_pick(DevTables tb, EccBuf eb, int ne, Ctl *ctl, int nslots = NX + 1)
 {
+    // nslots = NX+1: V_R over the vertices; 1: P_theta (only slot 0 is filled)
     const int lane = threadIdx.x & 31;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (e >= ne) return;
@@ -647,7 +653,7 @@ __global__ void k_ecc_pick(DevTables tb, EccBuf eb, int ne, Ctl *ctl)
     for (int c = lane; c < ncand; c += 32) {
         bool ok = true;
         double sum = 0.0;
-        for (int i = 0; i <= NX; ++i) {
+        for (int i = 0; i < nslots; ++i) {
             const size_t slot = ((size_t)e * ncand + c) * (NX + 2) + i;
             ok = ok && eb.S[slot] == 1;
             sum += eb.J[slot];

@@ -95,7 +95,24 @@ class HybridMPCProblem:
             if a.shape != shape:
                 raise ValueError('%s has shape %s, expected %s' % (nm, a.shape, shape))
             setattr(self, nm, a)
+        self.validate_unit_box()
         return self
+
+    def validate_unit_box(self):
+        """Every mode must carry the input-bound rows ``+-uhat_j <= 1`` (the reference's ``|u| <= u_max``
+        rows, ``lib/mpc_library.py:550-551``, in scaled inputs): the row pre-solve of the oracle kernels
+        (DESIGN.md "Row pre-solve") drops rows that cannot bind inside that box, which is exact only
+        if the box is part of the problem."""
+        for i in range(self.K):
+            for j in range(self.n_u):
+                for sgn in (1.0, -1.0):
+                    hit = [r for r in range(self.p)
+                           if not self.C[i, r].any() and sgn * self.D[i, r, j] > 0.0
+                           and np.count_nonzero(self.D[i, r]) == 1
+                           and self.e[i, r] <= abs(self.D[i, r, j]) * (1.0 + 1e-12)]
+                    if not hit:
+                        raise ValueError('mode %d has no row %+d*uhat_%d <= 1: scale the inputs so that '
+                                         'the input bounds are the unit box (u = u_scale * uhat)' % (i, int(sgn), j))
 
 
 def _discretize(A_c, B_c, w_c, h):
@@ -232,12 +249,14 @@ class InvertedPendulumOnCart:
 
 class SyntheticMPLP:
     """Synthetic multiparametric mixed-integer LP (no reference counterpart; SURVEY 8d
-    config 5): ``min c_k' z  s.t.  A_k z <= b_k + S_k theta``, z in R^nz, K one-hot modes,
-    N=1, theta in [-1,1]^n.  Seeded with ``numpy.random.default_rng(seed)``.  Data only in
-    round 1: the CPU oracle partitions it (tests/test_oracle_golden.py), the CUDA engine has no
-    kernel instantiation for NV = 25 yet (``ehm_problem_create`` rejects the shape)."""
+    config 5): ``min c_k' z  s.t.  A_k z <= b_k + S_k theta,  |z_j| <= zmax``, z in R^nz, K one-hot
+    modes, N=1, theta in [-1,1]^n.  Seeded with ``numpy.random.default_rng(seed)``.
 
-    def __init__(self, n=8, nz=16, rows=48, K=4, seed=20260922):
+    The engine variable is the SCALED input ``uhat = z / zmax`` so that the box rows read
+    ``|uhat_j| <= 1`` -- the convention of every :class:`HybridMPCProblem` (the row pre-solve of the
+    oracle kernels relies on the input box being the unit box, see ``validate_unit_box``)."""
+
+    def __init__(self, n=8, nz=16, rows=48, K=4, seed=20260922, zmax=10.0):
         rng = np.random.default_rng(seed)
         self.n_x, self.n_u, self.N, self.delta_size = n, nz, 1, K
         self.theta_scale = np.ones(n)
@@ -251,18 +270,17 @@ class SyntheticMPLP:
         S *= 0.9 / np.abs(S).sum(axis=2, keepdims=True)
         z0 = rng.standard_normal((K, nz))
         b = np.einsum('krz,kz->kr', A, z0) + 1.0 + np.abs(rng.standard_normal((K, rows)))
-        # box rows keep every LP bounded: |z_j| <= zmax
-        zmax = 10.0
+        # box rows keep every LP bounded: |z_j| <= zmax, i.e. |uhat_j| <= 1
         Abox = np.concatenate([np.eye(nz), -np.eye(nz)], axis=0)
-        A = np.concatenate([A, np.broadcast_to(Abox, (K,) + Abox.shape)], axis=1)
+        D = np.concatenate([A * zmax, np.broadcast_to(Abox, (K,) + Abox.shape)], axis=1)
         S = np.concatenate([S, np.zeros((K, 2 * nz, n))], axis=1)
-        b = np.concatenate([b, np.full((K, 2 * nz), zmax)], axis=1)
+        b = np.concatenate([b, np.ones((K, 2 * nz))], axis=1)
         self.problem = HybridMPCProblem(
             n_x=n, n_u=nz, N=1, K=K,
             A=np.zeros((K, n, n)), B=np.zeros((K, n, nz)), w=np.zeros((K, n)),
-            C=-S, D=A, e=b, Q=np.zeros((n, n)), P=np.zeros((n, n)),
-            R=np.zeros((nz, nz)), ru=c, u_scale=np.ones(nz), name='synthetic_mplp',
-            meta=dict(seed=seed)).validate()
+            C=-S, D=D, e=b, Q=np.zeros((n, n)), P=np.zeros((n, n)),
+            R=np.zeros((nz, nz)), ru=c * zmax, u_scale=np.full(nz, zmax), name='synthetic_mplp',
+            meta=dict(seed=seed, zmax=zmax)).validate()
 
 
 # name parity with the reference, where ExplicitMPC lives in lib/mpc_library.py:662-792

@@ -107,20 +107,70 @@ class Oracle:
         t = torch.where(st == 1, val, torch.full_like(val, float('nan')))
         return t, sol
 
+    # ------------------------------------------------------------------ batched reference calls
+    def _i32(self, B):
+        return torch.empty(B, dtype=torch.int32, device=self.device)
+
+    def P_theta_batch(self, theta):
+        """``ehm_p_theta_batch``: theta (B,n) -> CUDA tensors (cand int32 (B,), J (B,), u0hat (B,nu))."""
+        th = (theta if torch.is_tensor(theta) else self._dev(theta)).contiguous().view(-1, self.n)
+        B = th.shape[0]
+        cand, st = self._i32(B), self._i32(B)
+        J = torch.empty(B, dtype=torch.float64, device=self.device)
+        u0 = torch.zeros(B, self.nu, dtype=torch.float64, device=self.device)
+        _capi.check(_capi.lib().ehm_p_theta_batch(self._p.handle, B, th.data_ptr(), cand.data_ptr(),
+                                                  J.data_ptr(), u0.data_ptr(), st.data_ptr(), _stream()))
+        return cand, J, u0
+
+    def V_R_batch(self, R):
+        """``ehm_v_r_batch``: R (B,n+1,n) -> (cand (B,), Jv (B,n+1), Uvhat (B,n+1,nu))."""
+        Rt = (R if torch.is_tensor(R) else self._dev(R)).contiguous().view(-1, self.n + 1, self.n)
+        B = Rt.shape[0]
+        cand, st = self._i32(B), self._i32(B)
+        Jv = torch.empty(B, self.n + 1, dtype=torch.float64, device=self.device)
+        Uv = torch.zeros(B, self.n + 1, self.nu, dtype=torch.float64, device=self.device)
+        _capi.check(_capi.lib().ehm_v_r_batch(self._p.handle, B, Rt.data_ptr(), cand.data_ptr(),
+                                              Jv.data_ptr(), Uv.data_ptr(), st.data_ptr(), _stream()))
+        return cand, Jv, Uv
+
+    def bar_E_batch(self, R, Vr):
+        """``ehm_bar_e_batch``: (R (B,n+1,n), Vr (B,n+1)) -> (converged int32 (B,), tmin (B,))."""
+        Rt = (R if torch.is_tensor(R) else self._dev(R)).contiguous().view(-1, self.n + 1, self.n)
+        B = Rt.shape[0]
+        Vt = (Vr if torch.is_tensor(Vr) else self._dev(Vr)).contiguous().view(B, self.n + 1)
+        conv = self._i32(B)
+        tmin = torch.empty(B, dtype=torch.float64, device=self.device)
+        _capi.check(_capi.lib().ehm_bar_e_batch(self._p.handle, B, Rt.data_ptr(), Vt.data_ptr(),
+                                                conv.data_ptr(), tmin.data_ptr(), _stream()))
+        return conv, tmin
+
+    def bar_D_batch(self, R, Vr, cand_ref):
+        """``ehm_bar_d_batch`` -> (cand_star (B,), theta_star (B,n), Jv (B,n+1), Uvhat (B,n+1,nu),
+        var_small (B,), status (B,))."""
+        Rt = (R if torch.is_tensor(R) else self._dev(R)).contiguous().view(-1, self.n + 1, self.n)
+        B = Rt.shape[0]
+        Vt = (Vr if torch.is_tensor(Vr) else self._dev(Vr)).contiguous().view(B, self.n + 1)
+        cr = (cand_ref if torch.is_tensor(cand_ref) else self._dev(cand_ref, torch.int32)).contiguous().view(B)
+        cs, vs, st = self._i32(B), self._i32(B), self._i32(B)
+        ths = torch.zeros(B, self.n, dtype=torch.float64, device=self.device)
+        Jv = torch.zeros(B, self.n + 1, dtype=torch.float64, device=self.device)
+        Uv = torch.zeros(B, self.n + 1, self.nu, dtype=torch.float64, device=self.device)
+        _capi.check(_capi.lib().ehm_bar_d_batch(self._p.handle, B, Rt.data_ptr(), Vt.data_ptr(), cr.data_ptr(),
+                                                cs.data_ptr(), ths.data_ptr(), Jv.data_ptr(), Uv.data_ptr(),
+                                                vs.data_ptr(), st.data_ptr(), _stream()))
+        return cs, ths, Jv, Uv, vs, st
+
     # ------------------------------------------------------------------ reference API
     def P_theta(self, theta, check_feasibility=False):
         """``lib/oracle.py:104-139``: argmin over commutations (ties -> smallest index)."""
-        th = self._dev(theta).view(1, self.n).expand(self.ncand, -1).contiguous()
-        J, u0, st = self.point_batch(th, self._all)
-        ok = st == 1
+        cand, J, u0 = self.P_theta_batch(np.asarray(theta, dtype=float).reshape(1, -1))
+        c = int(cand[0].item())
         if check_feasibility:
-            return bool(ok.any().item())
-        if not bool(ok.any().item()):
+            return c >= 0
+        if c < 0:
             return None, None, np.inf, 0.0
-        Jm = torch.where(ok, J, torch.full_like(J, float('inf')))
-        c = int(torch.argmin(Jm).item())       # first minimum = smallest index
-        return (self.pb.u_scale * u0[c].cpu().numpy(), self.pb.commutation_from_index(c),
-                float(J[c].item()), 0.0)
+        return (self.pb.u_scale * u0[0].cpu().numpy(), self.pb.commutation_from_index(c),
+                float(J[0].item()), 0.0)
 
     def P_theta_delta(self, theta, delta, check_feasibility=False):
         """``lib/oracle.py:141-173``."""
@@ -137,57 +187,33 @@ class Oracle:
     def V_R(self, R):
         """``lib/oracle.py:175-218``.  Canonical rule: among candidates feasible (and
         convergent) at all n+1 vertices the one minimising the sum of vertex costs."""
-        J, u0, st = self._vertex_problems(R, self._all)
-        ok = (st == 1).all(dim=1)
-        if not bool(ok.any().item()):
+        cand, Jv, Uv = self.V_R_batch(np.asarray(R, dtype=float)[None])
+        c = int(cand[0].item())
+        if c < 0:
             return None, None
-        tot = torch.where(ok, J.sum(dim=1), torch.full((self.ncand,), float('inf'),
-                                                       dtype=torch.float64, device=self.device))
-        c = int(torch.argmin(tot).item())
-        Jc, uc = J[c].cpu().numpy(), u0[c].cpu().numpy()
+        Jc, uc = Jv[0].cpu().numpy(), Uv[0].cpu().numpy()
         return (self.pb.commutation_from_index(c),
                 [(self.pb.u_scale * uc[i], float(Jc[i]), 0.0) for i in range(self.n + 1)])
 
     def bar_E_delta_R(self, R, V_delta_R):
         """``lib/oracle.py:285-309``: True iff no commutation satisfies the two
         eps-improvement inequalities anywhere in R."""
-        t, _ = self._tstar_all(R, V_delta_R)
-        return not bool((t <= 0.0).any().item())
+        conv, _ = self.bar_E_batch(np.asarray(R, dtype=float)[None], np.asarray(V_delta_R, dtype=float)[None])
+        return bool(conv[0].item())
 
     def bar_D_delta_R(self, R, V_delta_R, delta_ref):
         """``lib/oracle.py:311-414`` (+ ``in_variability_ball`` :220-283)."""
         cref = self._cand_index(delta_ref)
-        Rn = np.asarray(R, dtype=float)
-        Vr = np.asarray(V_delta_R, dtype=float)
-        t, sol = self._tstar_all(Rn, Vr)
-        # delta_ref is feasible at every vertex by construction: no phase-1 for it
-        tr, solr, str_ = self.simplex_batch(Rn[None], Vr[None], np.array([cref], np.int32),
-                                            SX_TQP, False)
-        tref = float(tr[0].item()) if int(str_[0].item()) == 1 else float('inf')
-        tt = t.clone()
-        tt[cref] = float('nan')
-        better = (tt <= 0.0) & (tt < tref)
-        idx = torch.nonzero(better).flatten()
-        none = (None, None, None, None)
-        if idx.numel() == 0:
-            return none
-        order = idx[torch.argsort(tt[idx], stable=True)]
-        J, u0, st = self._vertex_problems(Rn, order.to(torch.int32))
-        ok = (st == 1).all(dim=1)
-        if not bool(ok.any().item()):
-            return none
-        k = int(torch.nonzero(ok).flatten()[0].item())
-        c = int(order[k].item())
-        mv, _, sm = self.simplex_batch(Rn[None], None, np.array([cref], np.int32), SX_MINV, False)
-        if int(sm[0].item()) != 1:
-            return none
-        s = sol[c].cpu().numpy()
-        theta_star = Rn[0] + (Rn[1:] - Rn[0]).T.dot(s[:self.n])
-        var_small = (Vr.max() - float(mv[0].item())) < max(self.eps_a, self.eps_r * s[self.n])
-        Jc, uc = J[k].cpu().numpy(), u0[k].cpu().numpy()
-        return (self.pb.commutation_from_index(c), theta_star,
+        cs, ths, Jv, Uv, vs, st = self.bar_D_batch(np.asarray(R, dtype=float)[None],
+                                                   np.asarray(V_delta_R, dtype=float)[None],
+                                                   np.array([cref], dtype=np.int32))
+        c = int(cs[0].item())
+        if c < 0:
+            return None, None, None, None
+        Jc, uc = Jv[0].cpu().numpy(), Uv[0].cpu().numpy()
+        return (self.pb.commutation_from_index(c), ths[0].cpu().numpy(),
                 [(self.pb.u_scale * uc[i], float(Jc[i]), 0.0) for i in range(self.n + 1)],
-                bool(var_small))
+                bool(vs[0].item()))
 
     def in_variability_ball(self, R, V_delta_R, delta_ref, delta_star, theta_star):
         """``lib/oracle.py:220-283``."""

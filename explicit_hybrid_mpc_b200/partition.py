@@ -12,6 +12,7 @@ objects (``lib/tree.py``) from the flat node store, so ``tree.pkl`` consumers ke
   reference's worker -> scheduler -> worker task hand-over (``lib/worker.py:187-239``).
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -122,6 +123,23 @@ class PartitionResult:
         return initial_tree
 
 
+def leafset_digest(left, root_id, vertices, nroots):
+    """Per root simplex: (number of leaves, sha256 of the lexicographically sorted leaf vertex sets,
+    raw fp64 bytes) -- independent of node numbering, so any two engines that build the same
+    partition agree on it bit for bit."""
+    import hashlib
+    left, root_id = np.asarray(left), np.asarray(root_id)
+    V = np.asarray(vertices, dtype=np.float64)
+    counts, digests = [], []
+    for r in range(nroots):
+        L = V[(left < 0) & (root_id == r)]
+        L = L.reshape(len(L), -1)
+        L = L[np.lexsort(L.T[::-1])] if len(L) else L
+        counts.append(int(len(L)))
+        digests.append(hashlib.sha256(np.ascontiguousarray(L).tobytes()).hexdigest())
+    return counts, digests
+
+
 def roots_of(initial_tree):
     """Root simplices (nroots,n+1,n) = the open leaves of the initial tree in depth-first
     order (``Scheduler.populate_queue``, ``lib/scheduler.py:620-642``)."""
@@ -196,7 +214,7 @@ class _Engine:
                    vertices=np.empty((nn, n + 1, n)), vcost=np.empty((nn, n + 1)),
                    vinput=np.empty((nn, n + 1, nu)))
         _capi.check(self.L.ehm_partition_fetch(self.h, *[arr[k].ctypes.data for k in _FIELDS]))
-        arr['vinput'] = arr['vinput'] * self.oracle.pb.u_scale
+        arr['vinput'] *= self.oracle.pb.u_scale          # in place: the store can be tens of GB
         if with_origin:
             org = np.empty((nn, 2), np.int32)
             _capi.check(self.L.ehm_partition_fetch_origin(self.h, org.ctypes.data))
@@ -420,6 +438,88 @@ def deal_plan(sizes):
 _CALLS = [0]
 
 
+class _ShmFlags:
+    """Starvation flags of one partition job in shared host memory (/dev/shm): all ranks of the
+    contract's single node map the same file, so polling after every wave is a local memory read
+    instead of a TCP round trip to the rendezvous store (round 1).  One int32 counter per meeting."""
+
+    SLOTS = 1 << 16
+
+    def __init__(self, name, rank, group):
+        import torch.distributed as dist
+        self.path = os.path.join('/dev/shm', name)
+        if rank == 0:
+            np.zeros(self.SLOTS, dtype=np.int32).tofile(self.path)
+        dist.barrier(group=group)
+        self.a = np.memmap(self.path, dtype=np.int32, mode='r+', shape=(self.SLOTS,))
+        self.rank = rank
+
+    def raised(self, meeting):
+        return int(self.a[meeting % self.SLOTS]) != 0
+
+    def raise_(self, meeting):
+        self.a[meeting % self.SLOTS] = 1
+
+    def close(self, group):
+        import torch.distributed as dist
+        dist.barrier(group=group)
+        del self.a
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def _pack_records(meta, geom, lb):
+    """one byte buffer per record: meta int32[6] | geom f64[ng] | lb f32[ncand]"""
+    import torch
+    k = meta.shape[0]
+    widths = (24, 8 * geom.shape[1], 4 * lb.shape[1])
+    if k == 0:
+        return torch.empty(0, sum(widths), dtype=torch.uint8, device=meta.device)
+    return torch.cat([t.contiguous().view(torch.uint8).view(k, w) for t, w in zip((meta, geom, lb), widths)],
+                     dim=1).contiguous()
+
+
+def _unpack_records(buf, ng, ncand):
+    import torch
+    k = buf.shape[0]
+    a, b = 24, 24 + 8 * ng
+    meta = buf[:, :a].contiguous().view(torch.int32).view(k, 6)
+    geom = buf[:, a:b].contiguous().view(torch.float64).view(k, ng)
+    lb = buf[:, b:].contiguous().view(torch.float32).view(k, ncand)
+    return meta, geom, lb
+
+
+def _gather_arrays(arr, rank, world, group, dev):
+    """Node arrays of every rank -> rank 0, as tensors (one uneven all-to-all per field over the
+    process group's backend; round 1 pickled the arrays through gather_object)."""
+    import torch
+    import torch.distributed as dist
+    n = torch.tensor([len(arr['left'])], dtype=torch.int64, device=dev)
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    sizes = [int(x) for x in sizes.tolist()]
+    parts = [dict() for _ in range(world)] if rank == 0 else None
+    for key in list(_FIELDS) + ['origin']:
+        a = np.ascontiguousarray(arr[key])
+        row = int(np.prod(a.shape[1:])) if a.ndim > 1 else 1
+        src = torch.from_numpy(a.reshape(len(a), row) if a.ndim > 1 else a.reshape(len(a), 1)).to(dev)
+        out_split = [s if rank == 0 else 0 for s in sizes]
+        in_split = [len(a)] + [0] * (world - 1)
+        dst = torch.empty((sum(out_split), row), dtype=src.dtype, device=dev)
+        dist.all_to_all_single(dst, src, out_split, in_split, group=group)
+        if rank == 0:
+            host = dst.cpu().numpy()
+            off = 0
+            for r in range(world):
+                parts[r][key] = host[off:off + sizes[r]].reshape((sizes[r],) + a.shape[1:])
+                off += sizes[r]
+        del src, dst
+    return parts
+
+
 def _default_store():
     import torch.distributed as dist
     try:
@@ -453,8 +553,16 @@ def partition_distributed(oracle, roots, group=None, waves_per_round=1, wave=0, 
     roots = np.ascontiguousarray(roots, dtype=np.float64)
     mine = shard_roots(roots, rank, world)
     eng = engine_cls(oracle, roots[mine], wave, max_nodes, max_frontier, 0, verbose, root_ids=mine)
-    store = _default_store() if signal else None
     _CALLS[0] += 1
+    flags = None
+    if signal and world > 1:
+        # one file per job: the rendezvous port makes the name unique per launch on this node
+        name = 'ehm_b200_%s_%d' % (os.environ.get('MASTER_PORT', 'p'), _CALLS[0])
+        try:
+            flags = _ShmFlags(name, rank, group)
+        except OSError:
+            flags = None
+    store = _default_store() if (signal and flags is None) else None
     prefix = 'ehm_b200/%d/' % _CALLS[0]
     fill = fill_depth
     sizes = torch.zeros(world, 2, dtype=torch.int64, device=dev)
@@ -472,7 +580,13 @@ def partition_distributed(oracle, roots, group=None, waves_per_round=1, wave=0, 
 
     try:
         while True:
-            if store is not None:
+            if flags is not None:
+                while True:
+                    mysize = eng.advance(waves_per_round)
+                    if mysize < fill or flags.raised(meetings):
+                        break
+                flags.raise_(meetings)
+            elif store is not None:
                 key = prefix + str(meetings)
                 while True:
                     mysize = eng.advance(waves_per_round)
@@ -510,13 +624,12 @@ def partition_distributed(oracle, roots, group=None, waves_per_round=1, wave=0, 
                 meta, geom, lb = meta[order].contiguous(), geom[order].contiguous(), lb[order].contiguous()
             nrecv = plan[:, rank]
             kr = int(nrecv.sum())
-            rmeta = torch.empty(kr, 6, dtype=torch.int32, device=dev)
-            rgeom = torch.empty(kr, eng.geom_width(), dtype=torch.float64, device=dev)
-            rlb = torch.empty(kr, eng.ncand, dtype=torch.float32, device=dev)
             ins, outs = [int(x) for x in nsend], [int(x) for x in nrecv]
-            dist.all_to_all_single(rmeta, meta, outs, ins, group=group)
-            dist.all_to_all_single(rgeom, geom, outs, ins, group=group)
-            dist.all_to_all_single(rlb, lb, outs, ins, group=group)
+            # one packed byte record per frontier entry, one all-to-all (round 1: three)
+            sbuf = _pack_records(meta, geom, lb)
+            rbuf = torch.empty(kr, sbuf.shape[1], dtype=torch.uint8, device=dev)
+            dist.all_to_all_single(rbuf, sbuf, outs, ins, group=group)
+            rmeta, rgeom, rlb = _unpack_records(rbuf, eng.geom_width(), eng.ncand)
             origin = torch.repeat_interleave(torch.arange(world, dtype=torch.int32, device=dev),
                                              torch.tensor(outs, device=dev))
             eng.import_(rmeta, rgeom, rlb, origin)
@@ -537,10 +650,11 @@ def partition_distributed(oracle, roots, group=None, waves_per_round=1, wave=0, 
     wall = time.perf_counter() - t0
     info = dict(rank=rank, world=world, wall_s=wall, exchange_s=xch_s, rounds=rounds,
                 meetings=meetings, records_sent=moved, stats=st, loop_device_ms=loop_ms)
+    if flags is not None:
+        flags.close(group)
     result = None
     if gather:
-        parts = [None] * world if rank == 0 else None
-        dist.gather_object(arr, parts, dst=0, group=group)
+        parts = _gather_arrays(arr, rank, world, group, dev)
         if rank == 0:
             merged = stitch(parts)
             result = PartitionResult(merged, dict(st), oracle.pb)

@@ -84,6 +84,39 @@ int ehm_simplex_batch(ehm_problem *p, int B, const double *d_R, const double *d_
                       const int *d_cand, int mode, int with_phase1, double *d_val,
                       double *d_sol, int *d_status, void *stream);
 
+/* ---- the reference's set-valued oracle calls, batched ----------------------------------
+ * MOSEK's branch and bound over the binary commutation is replaced by enumeration of all K^N
+ * one-hot commutations ("candidates") on the device, followed by device-side selection with the
+ * canonical rules of DESIGN.md.  All arrays are DEVICE pointers owned by the caller; scratch is
+ * kept (grow-only) inside the problem object.  Candidate index <-> commutation vector:
+ * base-K digits, step 0 most significant (mpc_library.HybridMPCProblem.commutation_from_index).
+ *
+ * Oracle.P_theta  [lib/oracle.py:104-139]: argmin over the commutations of the fixed-delta optimal
+ * cost at each of B parameters (ties -> smallest index).  d_cand[b] = -1 / d_status[b] = 0 when no
+ * commutation is feasible (the reference's check_feasibility=True answer is d_status).
+ * d_J, d_u0 (B,nu scaled first input), d_status may be NULL. */
+int ehm_p_theta_batch(ehm_problem *p, int B, const double *d_theta, int *d_cand, double *d_J,
+                      double *d_u0, int *d_status, void *stream);
+/* Oracle.V_R  [lib/oracle.py:175-218]: for each of B simplices d_R (B,n+1,n) the commutation that is
+ * feasible at all n+1 vertices with the smallest sum of vertex costs (-1: none; the reference then
+ * returns (None, None)), with its vertex costs d_Jv (B,n+1) and scaled inputs d_Uv (B,n+1,nu). */
+int ehm_v_r_batch(ehm_problem *p, int B, const double *d_R, int *d_cand, double *d_Jv, double *d_Uv,
+                  int *d_status, void *stream);
+/* Oracle.bar_E_delta_R  [lib/oracle.py:285-309]: d_converged[b] = 1 iff no commutation satisfies the
+ * two eps-improvement inequalities (:94-95) anywhere in simplex b, i.e. min_c t*_c > 0.
+ * d_tmin (optional): that minimum (+inf if no commutation is alive on the simplex). */
+int ehm_bar_e_batch(ehm_problem *p, int B, const double *d_R, const double *d_Vr, int *d_converged,
+                    double *d_tmin, void *stream);
+/* Oracle.bar_D_delta_R + in_variability_ball  [lib/oracle.py:311-414, 220-283]: delta* =
+ * argmin t*_c over the commutations that beat delta_ref (t*_c <= 0, t*_c < t*_ref) and are feasible
+ * at all vertices; -1 = the reference's (None, None, None, None).  Outputs for delta* != -1:
+ * d_theta_star (B,n) minimiser of its epigraph problem, d_Jv (B,n+1) / d_Uv (B,n+1,nu) its vertex
+ * costs / scaled inputs, d_var_small (B) the in_variability_ball verdict.  d_status (optional):
+ * 1 ok, -1 the min-over-simplex problem of delta_ref failed numerically (answer -1). */
+int ehm_bar_d_batch(ehm_problem *p, int B, const double *d_R, const double *d_Vr,
+                    const int *d_cand_ref, int *d_cand_star, double *d_theta_star, double *d_Jv,
+                    double *d_Uv, int *d_var_small, int *d_status, void *stream);
+
 /* Longest-edge bisection of B simplices  [lib/tools.py:224-257].  d_ij (B,2) int32. */
 int ehm_split_batch(int n, int B, const double *d_R, double *d_S1, double *d_S2, int *d_ij,
                     void *stream);
@@ -183,7 +216,7 @@ typedef struct ehm_locator ehm_locator;
 int ehm_locator_create(int n, int nu, int64_t nnodes, const int32_t *left, const int32_t *right,
                        const double *vertices, const double *vinput, int32_t top, ehm_locator **out);
 int ehm_locator_eval(ehm_locator *l, int64_t B, const double *d_theta, double *d_u, int32_t *d_leaf,
-                     cudaStream_t stream);
+                     void *stream);
 int ehm_locator_destroy(ehm_locator *l);
 
 #ifdef __cplusplus

@@ -28,3 +28,18 @@ def test_no_cpu_fallback():
     import pytest
     with pytest.raises(RuntimeError):
         Oracle(InvertedPendulumOnCart(), 1.0, 1.0)
+
+
+def test_header_is_plain_c():
+    """include/ehm.h is the drop-in boundary: it must compile as C (no CUDA or C++ types)."""
+    import subprocess
+    hdr = os.path.join(ROOT, 'include', 'ehm.h')
+    subprocess.check_call(['gcc', '-fsyntax-only', '-x', 'c', '-std=c99', '-Wall', '-Werror', hdr])
+
+
+def test_binding_covers_every_export():
+    """The ctypes binding names every symbol of the header (no hasattr guards)."""
+    from explicit_hybrid_mpc_b200 import _capi
+    hdr = open(os.path.join(ROOT, 'include', 'ehm.h')).read()
+    names = set(re.findall(r'\b(ehm_[a-z_0-9]+)\s*\(', hdr))
+    assert names <= set(_capi.EXPORTS), sorted(names - set(_capi.EXPORTS))

@@ -74,7 +74,7 @@ def test_tree_equals_cpu_oracle(sel, pendulum_roots, cpu_oracle, gpu_oracle):
 
 
 @pytest.mark.parametrize('fixture', ['worker_tree_golden.npz', 'worker_tree_golden_root0.npz',
-                                     'worker_tree_golden_deep.npz'])
+                                     'worker_tree_golden_deep.npz', 'worker_tree_golden_config3.npz'])
 def test_tree_equals_reference_worker_recursion(fixture, pendulum, pendulum_roots):
     """The device loop against the trees built by the REFERENCE'S OWN Worker.ecc / Worker.lcss /
     split code over the six-method oracle API (tests/golden/make_worker_golden.py): topology,
@@ -86,6 +86,49 @@ def test_tree_equals_reference_worker_recursion(fixture, pendulum, pendulum_root
     res = partition(Oracle(pendulum, eps_a, eps_r), roots, wave=128)
     assert res.stats['nfail'] == 0
     check_against_worker_golden(_gpu_arrays(res), z, len(roots), cost_rtol=1e-6, input_atol=2e-3)
+
+
+def test_ecc_split_branch_on_device():
+    """The ECC split branch of the device loop (k_ecc_final: no common commutation -> centroid
+    feasibility check, longest-edge split, both children re-queued for ECC; lib/worker.py:264-278)
+    against the tree the REFERENCE'S OWN Worker.ecc built on the two-mode toy problem
+    (tests/golden/toy_problem.py, make_worker_golden_toy.py).  No pendulum root takes this branch;
+    the toy root takes it at the root and again further down."""
+    import os
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from toy_problem import TOY_EPS, TOY_ROOT, toy_problem
+    from explicit_hybrid_mpc_b200.oracle import Oracle
+    from explicit_hybrid_mpc_b200.partition import partition
+    from test_oracle_golden import check_against_worker_golden
+
+    class _Mpc:
+        problem = toy_problem()
+        theta_scale = np.ones(2)
+    z = np.load(os.path.join(GOLDEN, 'worker_tree_golden_toy.npz'))
+    res = partition(Oracle(_Mpc(), TOY_EPS[0], TOY_EPS[1]), TOY_ROOT[None], wave=64)
+    assert res.stats['nfail'] == 0
+    g = _gpu_arrays(res)
+    assert (g['cand'][g['left'] >= 0] < 0).any(), 'no ECC split happened'
+    check_against_worker_golden(g, z, 1, cost_rtol=1e-6, input_atol=1e-5)
+
+
+def test_full_size_leaf_sets_equal_cpu_oracle(pendulum_roots, gpu_oracle):
+    """BASELINE config 2 at FULL size: per root simplex, the number of leaves and a hash of the sorted
+    leaf vertex sets equal the CPU oracle's (tests/golden/pendulum_full_leafsets.json, written by
+    scripts/make_full_leafsets.py from the CPU oracle alone) -- the bench partition is the oracle's,
+    leaf for leaf and bit for bit."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from explicit_hybrid_mpc_b200.partition import partition, leafset_digest
+    fx = json.load(open(os.path.join(GOLDEN, 'pendulum_full_leafsets.json')))
+    res = partition(gpu_oracle, pendulum_roots)
+    assert res.stats['nfail'] == 0
+    cnt, dig = leafset_digest(res.left, res.root_id, res.vertices, len(pendulum_roots))
+    assert cnt == fx['leaves_per_root']
+    assert dig == fx['sha256_per_root']
 
 
 @pytest.mark.parametrize('base', [22, 0])
@@ -130,9 +173,7 @@ def test_full_partition_invariants(pendulum, pendulum_roots, gpu_oracle):
     from explicit_hybrid_mpc_b200.partition import partition
     from explicit_hybrid_mpc_b200.tools import simplex_volume
     res = partition(gpu_oracle, pendulum_roots)
-    # numerical failures (a candidate treated as dead, cf. the reference's blacklist loop) are
-    # counted; a handful per 1.3e8 solves is tolerated here, 0 is required in the parity tests
-    assert res.stats['nfail'] <= 3
+    assert res.stats['nfail'] == 0
     leaves = res.leaf_ids()
     assert len(leaves) == res.stats['nleaves'] and len(leaves) > 10000
     assert res.closed[leaves].all()
@@ -167,3 +208,27 @@ def test_checkpoint_resume_equals_uninterrupted(tmp_path, pendulum_roots, gpu_or
     full = partition(gpu_oracle, roots)
     assert res.stats['nleaves'] == full.stats['nleaves'] and res.nnodes == full.nnodes
     compare_trees(_gpu_arrays(res), _gpu_arrays(full), 2)
+
+
+def test_synthetic_mplp_tree_equals_cpu_oracle():
+    """Second kernel shape (U=16, n=8: 25 variables, 91 rows; BASELINE config 5's problem family):
+    the device loop on a few Kuhn simplices of [-1,1]^8 against the CPU oracle, node for node."""
+    from explicit_hybrid_mpc_b200.mpc_library import SyntheticMPLP
+    from explicit_hybrid_mpc_b200.oracle import Oracle
+    from explicit_hybrid_mpc_b200.partition import partition
+    from explicit_hybrid_mpc_b200.tools import kuhn_triangulation
+    from oracle.oracle_cpu import CpuOracle
+    m = SyntheticMPLP()
+    roots = kuhn_triangulation(-np.ones(8), np.ones(8), limit=3)
+    eps_a, eps_r = 0.03, 0.01
+    res = partition(Oracle(m, eps_a, eps_r), roots, wave=256)
+    assert res.stats['nfail'] == 0
+    cpu = CpuOracle(m.problem, eps_a, eps_r, m.theta_scale).partition(roots, nthreads=8)
+    assert cpu['error'] == 0 and cpu['nfail'] == 0
+    assert res.stats['nleaves'] == cpu['nleaves'] and res.stats['nleaves'] > 3
+    g = _gpu_arrays(res)
+    g['vinput'] = g['vinput'] / m.problem.u_scale * 20.0 / 1e4   # compare_trees' input tolerance is the pendulum's
+    c = dict(cpu)
+    c['vinput'] = c['vinput'] / m.problem.u_scale * 20.0 / 1e4
+    worst = compare_trees(g, c, len(roots))
+    print('synthetic: nodes %d leaves %d worst rel cost diff %.2e' % (res.nnodes, res.stats['nleaves'], worst))
