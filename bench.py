@@ -67,16 +67,18 @@ class Workload:
                              '66 (BASELINE.json configs[2]; the whole Theta is ~6e7 leaves at this tolerance)')
             self.roots = allroots[self.root_ids]
             self.max_nodes = 1 << 22
+            self.max_frontier = 0
         elif config == 5:
             from explicit_hybrid_mpc_b200.mpc_library import SyntheticMPLP
             from explicit_hybrid_mpc_b200.tools import kuhn_triangulation
             self.mpc = SyntheticMPLP()
-            self.abs_frac, self.eps_a, self.eps_r = None, 0.01, 0.003
+            self.abs_frac, self.eps_a, self.eps_r = None, 0.038, 0.0114
             self.roots = kuhn_triangulation(-np.ones(8), np.ones(8), limit=1024)
             self.root_ids = list(range(1024))
             self.name = ('synthetic n=8 mp-LP (16 inputs, 80 rows, 4 modes, seed 20260922), first 1024 Kuhn '
-                         'simplices of [-1,1]^8, eps_a=0.01 eps_r=0.003 (BASELINE.json configs[4])')
-            self.max_nodes = 24 << 20
+                         'simplices of [-1,1]^8, eps_a=0.038 eps_r=0.0114: ~7e6 leaves (BASELINE.json configs[4])')
+            self.max_nodes = 40 << 20
+            self.max_frontier = 1 << 21
         else:
             raise SystemExit('unknown --config %r (2, 3 or 5)' % config)
         self.n, self.nu = self.mpc.problem.n_x, self.mpc.problem.n_u
@@ -93,10 +95,10 @@ class Workload:
         """Bounded sample of the workload for the CPU legs.  config 2: the cheapest root simplices
         by the leaf count of the oracle's full-size fixture, as many as keep `threads` host threads busy
         for about `seconds` (rate from a calibration run on the four cheapest: it under-estimates,
-        their small trees cannot feed many threads for long, hence the 1.5).  configs 3 / 5: a fixed
-        prefix of the root list, with a node budget."""
+        their small trees cannot feed many threads for long, hence the 1.5).  config 3: root simplex 22;
+        config 5: every 128th root simplex (the cost per root varies by orders of magnitude over the box)."""
         if self.config == 5:
-            return list(range(24))
+            return list(range(0, 1024, 128))
         if self.config == 3:
             return [0]          # index into self.roots: root simplex 22
         p = os.path.join(ROOT, 'tests', 'golden', 'pendulum_full_leafsets.json')
@@ -332,16 +334,17 @@ def main():
             dist.barrier()
         t0 = time.perf_counter()
         if world == 1:
-            res = partition(o, rts, wave=args.wave, max_nodes=max_nodes)
+            res = partition(o, rts, wave=args.wave, max_nodes=max_nodes, max_frontier=wl.max_frontier, pinned=True)
             info = dict(exchange_s=0.0, rounds=0, records_sent=0)
         else:
-            # one partition job over all ranks: sharded frontier + all-to-all rebalance; the
-            # stitched tree is gathered to rank 0 inside the timed region (end-to-end)
-            res, info = partition_distributed(o, rts, gather=True, wave=args.wave or 1024,
+            # one partition job over all ranks: sharded frontier + all-to-all rebalance; every rank
+            # copies its share of the node store to its own host buffers inside the timed region
+            # (the per-rank dump of SURVEY 8e(3); stitching to one forest is tests/test_gpu_distributed.py)
+            res, info = partition_distributed(o, rts, gather=False, pinned=True, wave=args.wave or 1024,
                                               waves_per_round=1 if args.round_ms <= 0 else 0,
                                               round_ms=args.round_ms, signal=args.round_ms <= 0,
                                               fill_depth=args.fill, deal_depth=args.deal,
-                                              max_nodes=max_nodes)
+                                              max_nodes=max_nodes, max_frontier=wl.max_frontier)
             if res is None:
                 res = type('R', (), dict(stats=info['stats'], nnodes=info['stats']['nnodes']))()
             else:
@@ -429,8 +432,8 @@ def main():
                    note='CPU restatement of the reference algorithm with all of this repository\'s condensing, '
                         'pre-solve and pruning (not MOSEK: ~10 solves/s/core, lib/post_process.py:328-330)')
         # the GPU on exactly the sample the CPU legs partition: a same-work ratio
-        rs = partition(orc, roots[sample], wave=args.wave, max_nodes=wl.max_nodes)
-        rs2 = partition(orc, roots[sample], wave=args.wave, max_nodes=wl.max_nodes)
+        rs = partition(orc, roots[sample], wave=args.wave, max_nodes=wl.max_nodes, max_frontier=wl.max_frontier)
+        rs2 = partition(orc, roots[sample], wave=args.wave, max_nodes=wl.max_nodes, max_frontier=wl.max_frontier)
         g = rs2.stats['nleaves'] / (rs2.stats['device_ms'] * 1e-3)
         same_sample = dict(sample=[wl.root_ids[i] for i in sample], gpu_leaves=int(rs2.stats['nleaves']),
                            cpu_leaves=int(c['leaves']), gpu_leaves_per_s=g, cpu_leaves_per_s=c['value'],

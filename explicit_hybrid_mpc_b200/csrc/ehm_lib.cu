@@ -620,7 +620,7 @@ extern "C" int ehm_partition_create(ehm_problem *p, int nroots, const double *ro
     const int n = tb.n, nu = tb.nu, ncand = tb.ncand;
     const int W = o.wave > 0 ? o.wave : 4096;
     const int64_t maxn = o.max_nodes > 0 ? o.max_nodes : (int64_t)1 << 22;
-    const int64_t fcap = o.max_frontier > 0 ? o.max_frontier : std::max<int64_t>(65536, 16 * (int64_t)W);
+    const int64_t fcap = o.max_frontier > 0 ? o.max_frontier : std::max<int64_t>(65536, 64 * (int64_t)W);
     if (maxn > 0x7ffffff0ll || fcap > 0x7ffffff0ll || nroots > maxn) return fail(EHM_EINVAL, "capacity too large");
     // device buffers (several GB) are recycled: ehm_partition_free parks one object per problem
     ehm_partition *t = nullptr;

@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--problem', type=str, default='pendulum', help='pendulum | synthetic')
     ap.add_argument('--nroots', type=int, default=8, help='synthetic: number of Kuhn simplices of [-1,1]^8')
     ap.add_argument('--node-budget', type=int, default=0)
+    ap.add_argument('--root-stride', type=int, default=1, help='synthetic: keep every k-th root simplex')
     a = ap.parse_args()
     from explicit_hybrid_mpc_b200.mpc_library import InvertedPendulumOnCart
     from explicit_hybrid_mpc_b200.oracle import Oracle
@@ -31,7 +32,7 @@ def main():
         from explicit_hybrid_mpc_b200.mpc_library import SyntheticMPLP
         from explicit_hybrid_mpc_b200.tools import kuhn_triangulation
         mpc = SyntheticMPLP()
-        roots = kuhn_triangulation(-np.ones(8), np.ones(8), limit=a.nroots)
+        roots = kuhn_triangulation(-np.ones(8), np.ones(8), limit=a.nroots)[::a.root_stride]
     else:
         mpc = InvertedPendulumOnCart()
         roots = np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', 'pendulum_roots.npy'))
@@ -48,6 +49,7 @@ def main():
         st['solves_per_s_device'] = st['nsolves'] / (st['device_ms'] * 1e-3)
         st['iters_per_solve'] = st['niters'] / max(1, st['nsolves'])
         print(json.dumps(st))
+        del res
 
 
 if __name__ == '__main__':
