@@ -67,6 +67,7 @@ class Workload:
                              '66 (BASELINE.json configs[2]; the whole Theta is ~6e7 leaves at this tolerance)')
             self.roots = allroots[self.root_ids]
             self.max_nodes = 1 << 22
+            self.wave_multi = 1024
             self.max_frontier = 0
         elif config == 5:
             from explicit_hybrid_mpc_b200.mpc_library import SyntheticMPLP
@@ -78,6 +79,7 @@ class Workload:
             self.name = ('synthetic n=8 mp-LP (16 inputs, 80 rows, 4 modes, seed 20260922), first 1024 Kuhn '
                          'simplices of [-1,1]^8, eps_a=0.038 eps_r=0.0114: ~7e6 leaves (BASELINE.json configs[4])')
             self.max_nodes = 40 << 20
+            self.wave_multi = 4096
             self.max_frontier = 1 << 21
         else:
             raise SystemExit('unknown --config %r (2, 3 or 5)' % config)
@@ -340,7 +342,7 @@ def main():
             # one partition job over all ranks: sharded frontier + all-to-all rebalance; every rank
             # copies its share of the node store to its own host buffers inside the timed region
             # (the per-rank dump of SURVEY 8e(3); stitching to one forest is tests/test_gpu_distributed.py)
-            res, info = partition_distributed(o, rts, gather=False, pinned=True, wave=args.wave or 1024,
+            res, info = partition_distributed(o, rts, gather=False, pinned=True, wave=args.wave or wl.wave_multi,
                                               waves_per_round=1 if args.round_ms <= 0 else 0,
                                               round_ms=args.round_ms, signal=args.round_ms <= 0,
                                               fill_depth=args.fill, deal_depth=args.deal,
@@ -502,7 +504,7 @@ def main():
                                  'rank 0 in the last step)'
                                  % (world, '' if args.round_ms <= 0 else ' / every %.0f ms' % args.round_ms,
                                     xch[-1].get('meetings', 0), xch[-1]['rounds'], xch[-1]['records_sent'])),
-                    wave=(args.wave or 4096) if world == 1 else (args.wave or 1024),
+                    wave=(args.wave or 4096) if world == 1 else (args.wave or wl.wave_multi),
                     l2='flushed between timed iterations (256 MiB write)'),
         e2e=dict(value=e2e, unit='leaves/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
         oracle_solves_per_s=solves_all / dev_s,

@@ -517,9 +517,13 @@ def _unpack_records(buf, ng, ncand):
     import torch
     k = buf.shape[0]
     a, b = 24, 24 + 8 * ng
-    meta = buf[:, :a].contiguous().view(torch.int32).view(k, 6)
-    geom = buf[:, a:b].contiguous().view(torch.float64).view(k, ng)
-    lb = buf[:, b:].contiguous().view(torch.float32).view(k, ncand)
+    def dense(t):   # a fresh row-major copy (.contiguous() / .clone() keep the row stride of a one-row slice)
+        out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+        out.copy_(t)
+        return out
+    meta = dense(buf[:, :a]).view(torch.int32).view(k, 6)
+    geom = dense(buf[:, a:b]).view(torch.float64).view(k, ng)
+    lb = dense(buf[:, b:]).view(torch.float32).view(k, ncand)
     return meta, geom, lb
 
 

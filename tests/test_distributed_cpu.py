@@ -243,3 +243,17 @@ def test_stitch_resolves_forwarding_chains():
                     for c in (m['left'][inner], m['right'][inner]))
     assert leaves == [(2.0, 3.0), (3.0, 4.0)]
     assert (m['closed'][m['left'] < 0] == 1).all() and not (m['closed'] == 2).any()
+
+
+def test_record_pack_roundtrip():
+    """frontier records travel as one packed byte row each (meta | geom | bounds); one-row buffers
+    were the trap: a one-row slice is 'contiguous' whatever its row stride."""
+    from explicit_hybrid_mpc_b200.partition import _pack_records, _unpack_records
+    for k in (0, 1, 2, 7):
+        meta = torch.arange(k * 6, dtype=torch.int32).view(k, 6)
+        geom = torch.randn(k, 30, dtype=torch.float64)
+        lb = torch.randn(k, 3125)
+        buf = _pack_records(meta, geom, lb)
+        assert buf.shape == (k, 24 + 8 * 30 + 4 * 3125)
+        m, g, l = _unpack_records(buf, 30, 3125)
+        assert torch.equal(m, meta) and torch.equal(g, geom) and torch.equal(l, lb)
