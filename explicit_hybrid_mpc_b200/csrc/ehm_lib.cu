@@ -121,44 +121,59 @@ k_simplex_batch(DevTables tb, int B, const double *__restrict__ R, const double 
     }
 }
 
-// Longest-edge bisection, one thread per simplex (lib/tools.py:224-257).  Edge length =
-// sqrt of a left-to-right chain of fused multiply-adds: the arithmetic of the reference's
-// la.norm(R[i]-R[j]) (numpy: sqrt(x.dot(x)), BLAS dot of a short vector), so that ties between
-// edges of equal length break exactly as in the reference; first maximum wins.
-__global__ void k_split_batch(int n, int B, const double *__restrict__ R, double *S1, double *S2,
-                              int *ij)
+// Longest-edge bisection (lib/tools.py:224-257): one warp per simplex, coalesced.  The (n+1)n
+// coordinates are read once, contiguously, into shared memory; lane q computes the length of edge q
+// (itertools.combinations order, as the reference enumerates them) -- the square root of a
+// left-to-right chain of fused multiply-adds, the arithmetic of the reference's la.norm(R[i]-R[j])
+// (numpy: sqrt(x.dot(x)), BLAS dot of a short vector), so that ties between edges of equal length
+// break exactly as in the reference; the first maximum wins (smallest edge index among the equal
+// maxima); both children are written back contiguously.  HBM-bound: 3 x 8 (n+1) n + 8 bytes per simplex.
+constexpr int kSplitWarps = 8;
+__global__ void __launch_bounds__(32 * kSplitWarps)
+k_split_batch(int n, int B, const double *__restrict__ R, double *S1, double *S2, int *ij)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const double *Rb = R + (size_t)b * (n + 1) * n;
-    int bi = 0, bj = 1;
-    double best = -1.0;
-    for (int i = 0; i <= n; ++i)
-        for (int j = i + 1; j <= n; ++j) {
+    __shared__ double sh[kSplitWarps][EHM_SPLIT_MAXN * (EHM_SPLIT_MAXN + 1)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int len = (n + 1) * n, nedges = (n + 1) * n / 2;
+    double *v = sh[warp];
+    for (long long b = (long long)blockIdx.x * kSplitWarps + warp; b < B; b += (long long)gridDim.x * kSplitWarps) {
+        const double *Rb = R + (size_t)b * len;
+        for (int e = lane; e < len; e += 32) v[e] = Rb[e];
+        __syncwarp();
+        double best = -1.0;
+        int bq = 0x7fffffff, bi = 0, bj = 1;
+        for (int q = lane; q < nedges; q += 32) {
+            // edge q -> (i, j), i < j, in combinations order
+            int i = 0, rem = q;
+            while (rem >= n - i) { rem -= n - i; ++i; }
+            const int j = i + 1 + rem;
             double acc = 0.0;
             for (int k = 0; k < n; ++k) {
-                const double d = __dsub_rn(Rb[i * n + k], Rb[j * n + k]);
+                const double d = __dsub_rn(v[i * n + k], v[j * n + k]);
                 acc = __fma_rn(d, d, acc);
             }
-            const double len = __dsqrt_rn(acc);
-            if (len > best) {
-                best = len;
-                bi = i;
-                bj = j;
-            }
+            const double l = __dsqrt_rn(acc);
+            if (l > best) { best = l; bq = q; bi = i; bj = j; }
         }
-    double *A = S1 + (size_t)b * (n + 1) * n, *Bq = S2 + (size_t)b * (n + 1) * n;
-    for (int e = 0; e < (n + 1) * n; ++e) {
-        A[e] = Rb[e];
-        Bq[e] = Rb[e];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ol = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oq = __shfl_xor_sync(0xffffffffu, bq, o), oi = __shfl_xor_sync(0xffffffffu, bi, o),
+                      oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (ol > best || (ol == best && oq < bq)) { best = ol; bq = oq; bi = oi; bj = oj; }
+        }
+        double *A = S1 + (size_t)b * len, *Bq = S2 + (size_t)b * len;
+        for (int e = lane; e < len; e += 32) {
+            const int row = e / n, k = e - row * n;
+            const double mid = __ddiv_rn(__dadd_rn(v[bi * n + k], v[bj * n + k]), 2.0);
+            A[e] = row == bi ? mid : v[e];
+            Bq[e] = row == bj ? mid : v[e];
+        }
+        if (lane == 0) {
+            ij[2 * b] = bi;
+            ij[2 * b + 1] = bj;
+        }
+        __syncwarp();
     }
-    for (int k = 0; k < n; ++k) {
-        const double mid = __ddiv_rn(__dadd_rn(Rb[bi * n + k], Rb[bj * n + k]), 2.0);
-        A[bi * n + k] = mid;
-        Bq[bj * n + k] = mid;
-    }
-    ij[2 * b] = bi;
-    ij[2 * b + 1] = bj;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -407,9 +422,10 @@ extern "C" int ehm_simplex_batch(ehm_problem *p, int B, const double *d_R, const
 extern "C" int ehm_split_batch(int n, int B, const double *d_R, double *d_S1, double *d_S2,
                                int *d_ij, void *stream)
 {
-    if (n < 1 || B < 0 || !d_R || !d_S1 || !d_S2 || !d_ij) return fail(EHM_EINVAL, "bad argument");
+    if (n < 1 || n > EHM_SPLIT_MAXN || B < 0 || !d_R || !d_S1 || !d_S2 || !d_ij) return fail(EHM_EINVAL, "bad argument");
     if (B == 0) return EHM_OK;
-    k_split_batch<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, B, d_R, d_S1, d_S2, d_ij);
+    const int grid = (int)std::min<long long>(((long long)B + kSplitWarps - 1) / kSplitWarps, 148ll * 16);
+    k_split_batch<<<grid, 32 * kSplitWarps, 0, (cudaStream_t)stream>>>(n, B, d_R, d_S1, d_S2, d_ij);
     g_launches++;
     EHM_CUDA(cudaGetLastError());
     return EHM_OK;

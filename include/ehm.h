@@ -117,7 +117,8 @@ int ehm_bar_d_batch(ehm_problem *p, int B, const double *d_R, const double *d_Vr
                     const int *d_cand_ref, int *d_cand_star, double *d_theta_star, double *d_Jv,
                     double *d_Uv, int *d_var_small, int *d_status, void *stream);
 
-/* Longest-edge bisection of B simplices  [lib/tools.py:224-257].  d_ij (B,2) int32. */
+/* Longest-edge bisection of B simplices  [lib/tools.py:224-257].  d_ij (B,2) int32; n <= EHM_SPLIT_MAXN. */
+#define EHM_SPLIT_MAXN 16
 int ehm_split_batch(int n, int B, const double *d_R, double *d_S1, double *d_S2, int *d_ij,
                     void *stream);
 
