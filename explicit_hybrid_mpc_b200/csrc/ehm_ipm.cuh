@@ -123,9 +123,18 @@ constexpr int tile_width(int nv)
     return t;
 }
 
+// Shapes compiled for LP costs only keep no Hessian in shared memory (5 KB of the 39 KB a problem
+// of the synthetic n=8 shape needs: 6 instead of 5 resident problems per SM).  Keyed on the
+// (variables, row capacity) pair of the solver block; ehm_problem_create refuses a QP cost there.
+template <int NV, int CAP>
+struct IpmHasH { static constexpr bool value = true; };
+template <> struct IpmHasH<25, 92> { static constexpr bool value = false; };
+template <> struct IpmHasH<17, 92> { static constexpr bool value = false; };
+
 // Per-warp shared-memory block of the solver (offsets in doubles from the block base).
 template <int NV, int CAP>
 struct IpmWs {
+    static constexpr bool kHasH = IpmHasH<NV, CAP>::value;
     static_assert(CAP % 4 == 0, "row capacity must be a multiple of the DMMA k-step");
     static constexpr int TW = tile_width(NV);    // row stride of the tile
     static constexpr int cA = (NV + 1) & ~1;     // column a = w * rp (even: a and w are stored as one double2)
@@ -141,7 +150,7 @@ struct IpmWs {
     static constexpr int oT = 0;                               // tile [CAP][TW] (+ over-read pad)
     static constexpr int oK = oT + CAP * TW + 8 * NBA;         // K ext [8*NBA][LS]: rows < NV = K / L, row cA = G'(w rp)
     static constexpr int oHs = oK + 8 * NBA * LS + 1;          // H [NV][HS]
-    static constexpr int oF = (oHs + NV * HS + 1) & ~1;        // f        (NVP)
+    static constexpr int oF = (oHs + (kHasH ? NV * HS : 0) + 1) & ~1;   // f        (NVP)
     static constexpr int oZ = oF + NVP;                        // z in/out (NVP)
     static constexpr int oDz = oZ + NVP;                       // dz       (NVP)
     static constexpr int oDiag = oDz + NVP;                    // original diagonal of K (NVP)
@@ -322,9 +331,10 @@ __device__ __forceinline__ double trisolve_rolled(const double *Ks, int lane, do
 // (sigma* <= -TAU_INT) and later iterations cannot change the answer (oracle/ehm_oracle.c:
 // qp_solve_x).  The objective returned in that case is the bound -TAU_INT.
 template <int NV, int CAP>
-__device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH, bool early = false)
+__device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH_, bool early = false)
 {
     using W = IpmWs<NV, CAP>;
+    const bool hasH = W::kHasH && hasH_;
     constexpr int TW = W::TW, MR = W::MR, LS = W::LS, NBA = W::NBA, NBB = W::NBB;
     constexpr int NVE = NV & ~1;   // even part of the columns (128-bit loads), NV - NVE = 0/1 tail
     double *T = w + W::oT, *Ks = w + W::oK, *zs = w + W::oZ, *dzs = w + W::oDz;

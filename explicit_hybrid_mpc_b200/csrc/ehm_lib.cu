@@ -25,7 +25,7 @@ using namespace ehm;
 #define EHM_FOR_EACH_CFG(X)                                                                      \
     X(0, 5, 4, 80, 4, EHM_CPS_PEND)  /* inverted pendulum, N=5: 217 rows in, 41-68 after the pre-solve   */ \
     X(1, 2, 2, 32, 4, 4)  /* two-mode toy problem of the ECC-split test (tests/golden)        */ \
-    X(2, 16, 8, 96, 1, 5) /* synthetic n=8 mp-LP: 91 rows, NV = 25       */
+    X(2, 16, 8, 92, 1, 6) /* synthetic n=8 mp-LP: 91 rows, NV = 25; LP costs only (IpmHasH) */
 
 template <int U_, int NX_, int CAP_, int WPC_, int CPS_>
 struct Shape {
@@ -284,6 +284,17 @@ extern "C" int ehm_problem_create(const ehm_problem_desc *desc, ehm_problem **ou
         snprintf(buf, sizeof buf, "problem shape U=%d n=%d has no compiled kernel (EHM_FOR_EACH_CFG)", cd.U,
                  cd.n);
         return fail(EHM_EINVAL, buf);
+    }
+    {
+        bool lp = true;
+        for (int i = 0; i < cd.n * cd.n && lp; ++i) lp = desc->Q[i] == 0.0 && desc->P[i] == 0.0;
+        for (int i = 0; i < cd.nu * cd.nu && lp; ++i) lp = desc->R[i] == 0.0;
+        bool lp_only = false;
+#define X(ID, UU, NN, CC, WW, PP) \
+    if (cfg == ID) lp_only = !IpmWs<UU + NN + 1, CC>::kHasH;
+        EHM_FOR_EACH_CFG(X)
+#undef X
+        if (lp_only && !lp) return fail(EHM_EINVAL, "this problem shape is compiled for LP costs only (Q = P = R = 0)");
     }
     double nc = 1;
     for (int k = 0; k < cd.N; ++k) nc *= cd.K;

@@ -196,9 +196,11 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
             fs[lane] = (lane < U) ? fv / cs : 0.0;
             zs[lane] = 0.0;
         }
-        for (int e = lane; e < NV * NV; e += 32) {
-            const int a = e / NV, b = e % NV;
-            Hs[a * W::HS + b] = (a < U && b < U) ? 2.0 * Mc[a * Y + b] / cs : 0.0;
+        if constexpr (W::kHasH) {
+            for (int e = lane; e < NV * NV; e += 32) {
+                const int a = e / NV, b = e % NV;
+                Hs[a * W::HS + b] = (a < U && b < U) ? 2.0 * Mc[a * Y + b] / cs : 0.0;
+            }
         }
         for (int r = lane; r < cnt; r += 32) T[r * TW + U] = 0.0;
         cst = Mc[(Y - 1) * Y + Y - 1];
@@ -432,32 +434,35 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         }
         fmine *= 2.0;
     }
-    for (int e = lane; e < NVS * NVS; e += 32) {
-        const int a = e / NVS, b = e % NVS;
-        double v = 0.0;
-        if (a < NB && b < NB) {
-            const int lo = a < b ? a : b, hi = a < b ? b : a;
-            if (hi < U) v = Mc[a * Y + b];
-            else if (lo < U) {   // u-beta block: sum_j Mut[lo][j] E[j][hi-U]
+    if constexpr (W::kHasH) {
+        for (int e = lane; e < NVS * NVS; e += 32) {
+            const int a = e / NVS, b = e % NVS;
+            double v = 0.0;
+            if (a < NB && b < NB) {
+                const int lo = a < b ? a : b, hi = a < b ? b : a;
+                if (hi < U) v = Mc[a * Y + b];
+                else if (lo < U) {   // u-beta block: sum_j Mut[lo][j] E[j][hi-U]
 #pragma unroll
-                for (int j = 0; j < NX; ++j) v = fma(Mc[lo * Y + U + j], Es[j * NX + hi - U], v);
-            } else {             // beta-beta block: sum_j E[j][a-U] W1[j][b-U]
+                    for (int j = 0; j < NX; ++j) v = fma(Mc[lo * Y + U + j], Es[j * NX + hi - U], v);
+                } else {             // beta-beta block: sum_j E[j][a-U] W1[j][b-U]
 #pragma unroll
-                for (int j = 0; j < NX; ++j) v = fma(Es[j * NX + a - U], W1[j * NX + b - U], v);
+                    for (int j = 0; j < NX; ++j) v = fma(Es[j * NX + a - U], W1[j * NX + b - U], v);
+                }
+                v *= 2.0;
             }
-            v *= 2.0;
+            Hs[a * HS + b] = v;
         }
-        Hs[a * HS + b] = v;
+        __syncwarp();
     }
-    __syncwarp();
     if (!tau) {
         double v = 0.0;
-        if (lane < NB) v = fmax(fabs(Hs[lane * HS + lane]), fabs(fmine));
+        if (lane < NB) v = fmax(W::kHasH ? fabs(Hs[lane * HS + lane]) : 0.0, fabs(fmine));
         cs = fmax(1.0, warp_max(v));
     }
     {
         const double ics = 1.0 / cs;
-        for (int e = lane; e < NVS * NVS; e += 32) Hs[(e / NVS) * HS + e % NVS] *= ics;
+        if constexpr (W::kHasH)
+            for (int e = lane; e < NVS * NVS; e += 32) Hs[(e / NVS) * HS + e % NVS] *= ics;
         if (lane < W::NVP) {
             fs[lane] = (lane < NB) ? fmine * ics : ((lane == NB && tau) ? 1.0 : 0.0);
             zs[lane] = 0.0;
@@ -485,8 +490,9 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
             double v = warp_sum(gb[i]) + fs[U + i];
-            if (tb.is_lp == 0)
-                for (int k = 0; k < NVS; ++k) v = fma(Hs[(U + i) * HS + k], zs[k], v);
+            if constexpr (W::kHasH)
+                if (tb.is_lp == 0)
+                    for (int k = 0; k < NVS; ++k) v = fma(Hs[(U + i) * HS + k], zs[k], v);
             gb[i] = cs * v;
             sg += fabs(gb[i]);
             p0 = fma(-gb[i], zs[U + i], p0);
