@@ -76,6 +76,7 @@ k_point_batch(DevTables tb, int B, const double *__restrict__ theta, const int *
     constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
+    unsigned tma_parity = warp_ws_init<U, NX, CAP>(ws, lane);
     for (;;) {
         const long long b = next_item(cnt, lane);
         if (b >= B) break;
@@ -102,6 +103,7 @@ k_simplex_batch(DevTables tb, int B, const double *__restrict__ R, const double 
     constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
+    unsigned tma_parity = warp_ws_init<U, NX, CAP>(ws, lane);
     for (;;) {
         const long long b = next_item(cnt, lane);
         if (b >= B) break;
@@ -111,7 +113,7 @@ k_simplex_batch(DevTables tb, int B, const double *__restrict__ R, const double 
             o = solve_simplex<U, NX, CAP>(tb, c, R + (size_t)b * (NX + 1) * NX,
                                          Vr ? Vr + (size_t)b * (NX + 1) : nullptr, mode,
                                          with_phase1 != 0, ws,
-                                         sol ? sol + (size_t)b * (NX + 1) : nullptr, lane);
+                                         sol ? sol + (size_t)b * (NX + 1) : nullptr, lane, tma_parity);
         account(cnt, o, lane);
         if (lane == 0) {
             status[b] = o.status;

@@ -162,13 +162,14 @@ k_lcss_ref(DevTables tb, NodeStore ns, WaveBuf wv, int W, Ctl *ctl, DevCounters 
     constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
+    unsigned tma_parity = warp_ws_init<U, NX, CAP>(ws, lane);
     for (;;) {
         const long long e = grab(&ctl->cur[0], lane);
         if (e >= W) break;
         const int nd = wv.node[e];
         const SolveOut o = solve_simplex<U, NX, CAP>(tb, ns.cand[nd], ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, false,
-                                                    ws, nullptr, lane);
+                                                    ws, nullptr, lane, tma_parity);
         account(cnt, o, lane, 1, ns.cand[nd], nd);
         if (lane == 0) wv.tref[e] = (o.status == 1) ? o.val : INFINITY;
         __syncwarp();
@@ -221,6 +222,7 @@ k_lcss_eval(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
     constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
+    unsigned tma_parity = warp_ws_init<U, NX, CAP>(ws, lane);
     const int nitems = ctl->nitems;
     for (;;) {
         const long long it = grab(&ctl->cur[1], lane);
@@ -229,7 +231,7 @@ k_lcss_eval(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt)
         const int nd = wv.node[ec.x];
         const SolveOut o = solve_simplex<U, NX, CAP>(tb, ec.y, ns.verts + (size_t)nd * (NX + 1) * NX,
                                                     ns.vcost + (size_t)nd * (NX + 1), EHM_SX_TQP, true, ws,
-                                                    wv.it_sol + (size_t)it * (NX + 1), lane,
+                                                    wv.it_sol + (size_t)it * (NX + 1), lane, tma_parity,
                                                     wv.it_pl + (size_t)it * (NX + 1));
         account(cnt, o, lane, 2, ec.y, nd);
         if (lane == 0) {
@@ -347,6 +349,7 @@ k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt
     constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
+    unsigned tma_parity = warp_ws_init<U, NX, CAP>(ws, lane);
     const int np = ctl->npitems;
     for (;;) {
         const long long q = grab(&ctl->cur[2], lane);
@@ -356,7 +359,7 @@ k_lcss_points(DevTables tb, NodeStore ns, WaveBuf wv, Ctl *ctl, DevCounters *cnt
         SolveOut o;
         if (pi.i < 0) {
             o = solve_simplex<U, NX, CAP>(tb, pi.c, ns.verts + (size_t)nd * (NX + 1) * NX, nullptr,
-                                         EHM_SX_MINV, false, ws, nullptr, lane);
+                                         EHM_SX_MINV, false, ws, nullptr, lane, tma_parity);
             if (lane == 0) {
                 wv.minv[pi.e] = o.val;
                 wv.minv_st[pi.e] = o.status;
@@ -596,6 +599,7 @@ k_ecc_points(DevTables tb, NodeStore ns, EccBuf eb, int q0, int ne, int centroid
     constexpr int U = SH::U, NX = SH::NX, CAP = SH::CAP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ws = smem + (size_t)warp * WarpWs<U, NX, CAP>::kDoubles;
+    unsigned tma_parity = warp_ws_init<U, NX, CAP>(ws, lane);
     const int ncand = tb.ncand;
     const long long per = centroid ? ncand : (long long)ncand * (NX + 1);
     const long long total = per * ne;

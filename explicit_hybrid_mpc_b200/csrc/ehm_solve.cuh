@@ -59,9 +59,50 @@ struct WarpWs {
     static constexpr int oV = oE + NX * NX;          // Vr (NX+1)
     static constexpr int oW1 = oV + NX + 1;          // M_thth E (NX*NX)
     static constexpr int oW2 = oW1 + NX * NX;        // M_thth v0 + m_th (NX), theta scratch (NX)
-    static constexpr int kDoubles = (oW2 + 2 * NX + 1) & ~1;
+    // TMA staging of the candidate's cost matrix M (Y*Y doubles, one contiguous block in the
+    // table): cp.async.bulk needs 16-byte sizes and addresses, i.e. an even Y
+    static constexpr bool kTma = (Y * Y * 8) % 16 == 0;
+    static constexpr int oMst = (oW2 + 2 * NX + 1) & ~1;            // staged M (16-byte aligned)
+    static constexpr int oBar = oMst + (kTma ? Y * Y : 0);         // mbarrier (8 bytes)
+    static constexpr int kDoubles = (oBar + (kTma ? 1 : 0) + 1) & ~1;
     static_assert(WP::kDoubles <= WS::kDoubles, "point block must fit the simplex block");
 };
+
+// ---- TMA (bulk async copy) of one contiguous global block into shared memory ------------------
+// One elected lane arms the warp's mbarrier with the byte count and issues cp.async.bulk; the
+// copy runs behind the row assembly and the phase-1 solve, every lane waits on the barrier's
+// phase before the first use.  SASS: UBLKCP + SYNCS.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_bar_init(void *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra D_%=;\n"
+        "bra W_%=;\n"
+        "D_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// once per warp and kernel: arm the warp's mbarrier; returns the initial phase parity
+template <int U, int NX, int CAP>
+__device__ __forceinline__ unsigned warp_ws_init(double *ws, int lane);
 
 struct SolveOut {
     int status;   // 1 ok / feasible, 0 infeasible / not alive, -1 numerical failure
@@ -70,6 +111,17 @@ struct SolveOut {
     int nsolves;  // IPM solves spent
     double flops; // algorithmic flops spent (see ipm_solve)
 };
+
+template <int U, int NX, int CAP>
+__device__ __forceinline__ unsigned warp_ws_init(double *ws, int lane)
+{
+    using WW = WarpWs<U, NX, CAP>;
+    if constexpr (WW::kTma) {
+        if (lane == 0) tma_bar_init(ws + WW::oBar);
+        __syncwarp();
+    }
+    return 0u;
+}
 
 template <int NV, int CAP>
 __device__ __forceinline__ int run_ipm(double *ws, int m, int lane, bool hasH, SolveOut &out, double &obj,
@@ -241,7 +293,7 @@ __device__ SolveOut solve_point(const DevTables &tb, int c, const double *__rest
 template <int U, int NX, int CAP>
 __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__restrict__ Rv,
                                   const double *__restrict__ Vr, int mode, bool phase1,
-                                  double *ws, double *sol, int lane, float *plane = nullptr)
+                                  double *ws, double *sol, int lane, unsigned &tma_parity, float *plane = nullptr)
 {
     using WW = WarpWs<U, NX, CAP>;
     using W = typename WW::WS;
@@ -252,6 +304,27 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
     const int MP = tb.MP, m = tb.m;
     const double *Gc = tb.G + (size_t)c * U * MP, *Sc = tb.S + (size_t)c * NX * MP,
                  *gc = tb.g + (size_t)c * MP, *rc = tb.rho + (size_t)c * MP;
+    // the candidate's cost matrix travels by TMA behind the row assembly and the phase-1 solve
+    const double *Mg = tb.M + (size_t)c * Y * Y;
+    bool tma_pending = false;
+    if constexpr (WW::kTma) {
+        if (mode != EHM_SX_ALIVE) {
+            if (lane == 0) tma_load_1d(ws + WW::oMst, Mg, Y * Y * 8, ws + WW::oBar);
+            tma_pending = true;
+        }
+    }
+    // every exit drains the copy (a CTA must not retire, nor the barrier be re-armed, with a bulk
+    // copy in flight); tma_parity = phase parity of the next completion of this warp's barrier
+    auto leave = [&](const SolveOut &o) {
+        if constexpr (WW::kTma) {
+            if (tma_pending) {
+                tma_wait(ws + WW::oBar, tma_parity);
+                tma_parity ^= 1u;
+            }
+        }
+        __syncwarp();
+        return o;
+    };
     // simplex geometry: E[j][i] = v_{i+1}[j] - v_0[j]
     for (int e = lane; e < (NX + 1) * NX; e += 32) Rs[e] = Rv[e];
     if (mode == EHM_SX_TQP && lane <= NX) Vs[lane] = Vr[lane];
@@ -329,12 +402,12 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         }
         cnt += __popc(bal);
     }
-    if (__any_sync(kFull, viol)) return out;
+    if (__any_sync(kFull, viol)) return leave(out);
     // ---- simplex rows (-beta_i <= 0, sum beta <= 1) and the two epigraph rows ---------------
     const int nextra = NX + 1 + (tau ? 2 : 0);
     if (cnt + nextra > CAP) {
         out.status = -1;
-        return out;
+        return leave(out);
     }
     if (lane < nextra) {
         const int pos = cnt + lane;
@@ -387,21 +460,27 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
         const int st = run_ipm<NVS, CAP>(ws, n1rows, lane, false, out, obj, true);
         if (st != 0) {
             out.status = -1;
-            return out;
+            return leave(out);
         }
         if (mode == EHM_SX_ALIVE) {
             out.val = obj;
             out.status = (obj <= -EHM_TAU_INT) ? 1 : 0;
-            return out;
+            return leave(out);
         }
-        if (!(obj <= -EHM_TAU_INT)) return out;
+        if (!(obj <= -EHM_TAU_INT)) return leave(out);
         for (int r = lane; r < n1rows; r += 32) T[r * TW + NB] = 0.0;
         __syncwarp();
     }
     // ---- cost in [u; beta; 1]:  V = x'Mx, x = [u; theta; 1], theta = v0 + E beta ---------------
     //   H_uu = 2 Muu, H_ub = 2 Mut E, H_bb = 2 E' Mtt E, f_u = 2 (Mut v0 + mu),
     //   f_b = 2 E' (Mtt v0 + mt), const = v0' Mtt v0 + 2 mt' v0 + m0
-    const double *Mc = tb.M + (size_t)c * Y * Y;
+    const double *Mc = Mg;
+    if constexpr (WW::kTma) {
+        tma_wait(ws + WW::oBar, tma_parity);
+        tma_parity ^= 1u;
+        tma_pending = false;
+        Mc = ws + WW::oMst;
+    }
     for (int e = lane; e < NX * NX + NX; e += 32) {
         if (e < NX * NX) {
             const int a = e / NX, i = e % NX;   // W1[a][i] = sum_j Mtt[a][j] E[j][i]
@@ -472,7 +551,7 @@ __device__ SolveOut solve_simplex(const DevTables &tb, int c, const double *__re
     const int st = run_ipm<NVS, CAP>(ws, total, lane, tb.is_lp == 0, out, obj);
     if (st != 0) {
         out.status = -1;
-        return out;
+        return leave(out);
     }
     out.status = 1;
     out.val = cs * obj + cst;
