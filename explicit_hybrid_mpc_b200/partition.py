@@ -102,6 +102,34 @@ class PartitionResult:
                     max_depth=int(self.depth.max()), oracle_solves=int(st.get('nsolves', 0)),
                     oracle_failures=int(st.get('nfail', 0)))
 
+    def statistics_record(self, total_volume=None, ranks=None):
+        """One record of the reference's ``statistics.pkl`` (``lib/scheduler.py:293-308``):
+        ``dict(overall=..., process=[...])``.  ``process`` has one entry per GPU rank (``ranks``: the
+        per-rank stats dicts of a multi-GPU run, default this result's own) with the fields of the
+        reference's worker status (``lib/worker.py:31-116``) that have a device counterpart."""
+        o = self.overall_status(total_volume)
+        o['scheduler_looprate'] = dict(publisher=0.0, dispatcher=0.0, collector=0.0)   # no scheduler threads here
+        procs = []
+        for st in (ranks if ranks is not None else [self.stats]):
+            ms = list(st.get('stage_ms', [0.0] * 8))
+            procs.append(dict(status='idle', algorithm=None, current_branch='', current_location='',
+                              volume_filled_total=o['volume_filled_total'] if ranks is None else None,
+                              volume_filled_current=0.0, simplex_count_total=int(st.get('nleaves', 0)),
+                              simplex_count_current=0, time_active_total=float(st.get('device_ms', 0.0)) * 1e-3,
+                              time_active_current=0.0, time_idle=0.0, time_ecc=ms[7] * 1e-3,
+                              time_lcss=sum(ms[:7]) * 1e-3, oracle_solves=int(st.get('nsolves', 0)),
+                              oracle_failures=int(st.get('nfail', 0))))
+        return dict(overall=o, process=procs)
+
+    def append_statistics(self, path, total_volume=None, ranks=None):
+        """Append one record to a ``statistics.pkl``-style file (the reference appends a pickle per
+        publisher tick, ``lib/scheduler.py:306-308``; ``post_process.py:99-128`` reads them back one by one)."""
+        import pickle
+        rec = self.statistics_record(total_volume, ranks)
+        with open(path, 'ab') as f:
+            pickle.dump(rec, f)
+        return rec
+
     def write_status(self, path, total_volume=None):
         """``status.txt`` in the reference's layout (``lib/scheduler.py:311-333``, overall part)."""
         o = self.overall_status(total_volume)
