@@ -444,7 +444,12 @@ __global__ void k_lcss_final(DevTables tb, NodeStore ns, Frontier fr, WaveBuf wv
         double Vr[NX + 1];
         for (int i = 0; i <= NX; ++i) Vr[i] = ns.vcost[(size_t)nd * (NX + 1) + i];
         double rebase = 0.0;
-        if (kstar >= 0 && wv.minv_st[e] == 1) {
+        // delta* is adopted only if its follow-up problems went through: min_R V*_ref (in_variability_ball)
+        // and its own midpoint problem.  A numerical failure of either (counted in nfail by the solving
+        // kernel) falls back to delta_ref for this visit -- the reference's "blacklist delta* and retry"
+        // (lib/oracle.py:398-414); EHM_ENUMERIC is left for a failing midpoint of delta_ref itself.
+        if (kstar >= 0 && wv.minv_st[e] == 1 &&
+            wv.ptS[((size_t)e * (kSelT + 1) + kstar) * (NX + 2) + NX + 1] == 1) {
             cstar = wv.sel[e * kSelT + kstar];
             const int item = wv.titem[(size_t)e * ncand + cstar];
             const double Vstar = wv.it_sol[(size_t)item * (NX + 1) + NX];

@@ -1141,7 +1141,22 @@ static void lcss_step(builder *b, long id, double *lb)
         free(lb);
         return;
     }
-    int cnew = cref;
+    int cnew = cref, have_mid = 0;
+    double Jmid = 0, Umid[MAXNV];
+    if (res.cstar >= 0 && !res.var_small) {
+        /* delta* is adopted only if its own midpoint problem goes through; a numerical failure falls
+         * back to delta_ref for this visit (the reference's "blacklist delta* and retry",
+         * lib/oracle.py:398-414) -- same rule as k_lcss_final of the CUDA engine */
+        double T1[MAXNV * MAXNV], T2[MAXNV * MAXNV];
+        int tij[2];
+        ehmo_split(n, R, T1, T2, tij);
+        if (ehmo_p_theta_delta(pb, T1 + tij[0] * n, res.cstar, &Jmid, Umid) != 1) {
+            __sync_fetch_and_add(&t->nfail, 1);
+            res.cstar = -1;
+        } else {
+            have_mid = 1;
+        }
+    }
     if (res.cstar >= 0) { /* worker.py:389-395 */
         cnew = res.cstar;
         ehmo_lb_rebase(n, nc, Vr, Jn, lb);
@@ -1160,7 +1175,10 @@ static void lcss_step(builder *b, long id, double *lb)
     double S1[MAXNV * MAXNV], S2[MAXNV * MAXNV], Jm, Um[MAXNV];
     int ij[2];
     ehmo_split(n, R, S1, S2, ij);
-    if (ehmo_p_theta_delta(pb, S1 + ij[0] * n, cnew, &Jm, Um) != 1) {
+    if (have_mid) {
+        Jm = Jmid;
+        memcpy(Um, Umid, sizeof(double) * nu);
+    } else if (ehmo_p_theta_delta(pb, S1 + ij[0] * n, cnew, &Jm, Um) != 1) {
         t->error = 2; /* cannot happen for a convex feasible set; the reference would raise */
         free(lb);
         return;
