@@ -35,6 +35,10 @@
 
 #include "../../include/ehm.h"
 
+#ifndef EHM_SMALL_NV
+#define EHM_SMALL_NV 25   // systems up to this size: fully unrolled Cholesky / solves, own row in registers (NV = 25: -16 % vs rolled)
+#endif
+
 namespace ehm {
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -528,7 +532,7 @@ __device__ __noinline__ int ipm_solve(double *w, int m, int lane, bool hasH_, bo
         __syncwarp();
         const double ak = lane < NV ? Ks[W::cA * LS + lane] : 0.0;   // (G'(w rp))_k
         // ---- Cholesky, lane i = row i, left-looking, in place ------------------------------------
-        constexpr bool kSmall = NV <= 12;
+        constexpr bool kSmall = NV <= EHM_SMALL_NV;
         double Lr[kSmall ? NV : 1];
         double myinv;
         bool bad;

@@ -550,41 +550,50 @@ __global__ void k_lcss_final(DevTables tb, NodeStore ns, Frontier fr, WaveBuf wv
             fr.lb[(size_t)pos * ncand + c] = v0;
             fr.lb[(size_t)(pos + 1) * ncand + c] = v1;
         }
-        if (lane == 0) {
-            const int bi = wv.ij[2 * e], bj = wv.ij[2 * e + 1];
+        {
+            // children: vertices, vertex costs and vertex inputs are copied by the whole warp
+            // (round 1: lane 0 alone -- 2 x (n+1)(n + 1 + nu) doubles, 450 for the synthetic shape)
+            const int bi = sbi, bj = sbj;
             const double *R = ns.verts + (size_t)nd * (NX + 1) * NX;
             const int dep = ns.depth[nd] + 1;
-            atomicMax(&ctl->max_depth, dep);
-            ns.left[nd] = id0;
-            ns.right[nd] = id0 + 1;
+            if (lane == 0) {
+                atomicMax(&ctl->max_depth, dep);
+                ns.left[nd] = id0;
+                ns.right[nd] = id0 + 1;
+            }
             for (int side = 0; side < 2; ++side) {
                 const int ch = id0 + side, rep = side ? bj : bi;
                 double *Rc = ns.verts + (size_t)ch * (NX + 1) * NX;
-                for (int q = 0; q < (NX + 1) * NX; ++q) Rc[q] = R[q];
-                for (int k = 0; k < NX; ++k) Rc[rep * NX + k] = wv.vmid[e * NX + k];
-                for (int i = 0; i <= NX; ++i) {
+                for (int q = lane; q < (NX + 1) * NX; q += 32) {
+                    const int row = q / NX, k = q - row * NX;
+                    Rc[q] = row == rep ? wv.vmid[e * NX + k] : R[q];
+                }
+                for (int i = lane; i <= NX; i += 32) {
                     const bool mid = (i == rep);
                     const size_t src = mid ? pslot + NX + 1 : pslot + i;
-                    // costs/inputs: delta* values when switching, the node's own otherwise
-                    double Jv;
-                    if (cstar >= 0 || mid) Jv = wv.ptJ[src];
-                    else Jv = Vr[i];
-                    ns.vcost[(size_t)ch * (NX + 1) + i] = Jv;
-                    for (int q = 0; q < nu; ++q)
-                        ns.vinput[((size_t)ch * (NX + 1) + i) * nu + q] =
-                            (cstar >= 0 || mid) ? wv.ptU[src * nu + q]
-                                                : ns.vinput[((size_t)nd * (NX + 1) + i) * nu + q];
+                    // costs: delta* values when switching, the node's own otherwise
+                    ns.vcost[(size_t)ch * (NX + 1) + i] = (cstar >= 0 || mid) ? wv.ptJ[src] : ns.vcost[(size_t)nd * (NX + 1) + i];
                 }
-                ns.cand[ch] = cnew;
-                ns.left[ch] = -1;
-                ns.right[ch] = -1;
-                ns.root_id[ch] = ns.root_id[nd];
-                ns.depth[ch] = dep;
-                ns.closed[ch] = 0;
-                ns.origin[2 * ch] = -1;
-                ns.origin[2 * ch + 1] = -1;
-                fr.node[pos + side] = ch;
-                fr.skip[pos + side] = 0;
+                for (int q = lane; q < (NX + 1) * nu; q += 32) {
+                    const int i = q / nu, qq = q - i * nu;
+                    const bool mid = (i == rep);
+                    const size_t src = mid ? pslot + NX + 1 : pslot + i;
+                    ns.vinput[((size_t)ch * (NX + 1) + i) * nu + qq] =
+                        (cstar >= 0 || mid) ? wv.ptU[src * nu + qq]
+                                            : ns.vinput[((size_t)nd * (NX + 1) + i) * nu + qq];
+                }
+                if (lane == 0) {
+                    ns.cand[ch] = cnew;
+                    ns.left[ch] = -1;
+                    ns.right[ch] = -1;
+                    ns.root_id[ch] = ns.root_id[nd];
+                    ns.depth[ch] = dep;
+                    ns.closed[ch] = 0;
+                    ns.origin[2 * ch] = -1;
+                    ns.origin[2 * ch + 1] = -1;
+                    fr.node[pos + side] = ch;
+                    fr.skip[pos + side] = 0;
+                }
             }
         }
     }
