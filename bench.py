@@ -11,7 +11,7 @@ Workloads (``--config``, numbering of SURVEY.md section 8d):
      (the reference's own pairing, lib/post_process.py:334-338), 66 Delaunay root simplices.
      The partition is checked leaf for leaf against the CPU oracle's full-size fixture.
   3  BASELINE configs[2]: the same pendulum at abs_frac 0.03 / eps_r 0.05 (eps_a = 0.27937 by
-     examples.create_oracle), root simplices 22-25 (the whole Theta at this tolerance is ~6e7 leaves).
+     examples.create_oracle), root simplex 22: 114 076 leaves (the whole Theta at this tolerance is ~6e7).
   5  BASELINE configs[4]: synthetic n=8 mp-LP, 4 modes, first 1024 Kuhn simplices of [-1,1]^8,
      eps tuned to >= 10^6 leaves -- the scaling workload (a job long enough to shard over 8 GPUs).
 Default: config 5 at every N (the configuration the metric "at 1/2/4/8 B200" is quoted on), with the
@@ -62,9 +62,9 @@ class Workload:
                              '(BASELINE.json configs[1])')
             else:
                 self.abs_frac, self.eps_a, self.eps_r = 0.03, EPS_A_CONFIG3, 0.05
-                self.root_ids = [22, 23, 24, 25]
-                self.name = ('pendulum N=5 abs_frac=0.03 eps_r=0.05 (eps_a=0.27937), root simplices 22-25 of the '
-                             '66 (BASELINE.json configs[2]; the whole Theta is ~6e7 leaves at this tolerance)')
+                self.root_ids = [22]
+                self.name = ('pendulum N=5 abs_frac=0.03 eps_r=0.05 (eps_a=0.27937), root simplex 22 of the 66: '
+                             '114 076 leaves, depth 29 (BASELINE.json configs[2]; the whole Theta is ~6e7 leaves at this tolerance)')
             self.roots = allroots[self.root_ids]
             self.max_nodes = 1 << 22
             self.wave_multi = 1024
