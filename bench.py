@@ -462,6 +462,7 @@ def main():
                          ms_per_step=float(np.mean(ms2)), steps=2, warmup=2, leaves_per_step=int(rr.stats['nleaves']),
                          nfail=int(rr.stats['nfail']), parity=par,
                          oracle_solves_per_s=rr.stats['nsolves'] / (rr.stats['device_ms'] * 1e-3),
+                         solves_per_leaf=rr.stats['nsolves'] / max(rr.stats['nleaves'], 1),
                          roofline=_roofline(rr.stats, fp64_peak, 2))
         del o2, rr
 
@@ -507,7 +508,7 @@ def main():
                     wave=(args.wave or 4096) if world == 1 else (args.wave or wl.wave_multi),
                     l2='flushed between timed iterations (256 MiB write)'),
         e2e=dict(value=e2e, unit='leaves/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
-        oracle_solves_per_s=solves_all / dev_s,
+        oracle_solves_per_s=solves_all / dev_s, solves_per_leaf=solves_all / max(leaves_all, 1.0),
         gpu_launches=int(launches_all),
         clocks=_clocks_summary(samples),
         roofline=roofline, roofline_hbm=roofline_hbm, cpu_baseline=cpu, same_sample=same_sample,

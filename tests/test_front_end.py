@@ -70,3 +70,16 @@ def test_statistics_record_fields(tmp_path):
         assert key in rec['overall']
     assert rec['overall']['simplex_count_total'] == int((z['leaf'] & z['closed']).sum())
     assert rec['process'][0]['simplex_count_total'] == int(z['leaf'].sum())
+
+
+def test_unit_box_convention_is_enforced():
+    """HybridMPCProblem.validate: every mode must carry +-uhat_j <= 1 (the row pre-solve relies on it)."""
+    import pytest
+    from explicit_hybrid_mpc_b200.mpc_library import HybridMPCProblem, SyntheticMPLP
+    m = SyntheticMPLP(n=3, nz=4, rows=6, K=2, seed=1).problem       # valid by construction
+    assert m.p == 6 + 8 and np.allclose(m.u_scale, 10.0)
+    bad = HybridMPCProblem(n_x=m.n_x, n_u=m.n_u, N=1, K=m.K, A=m.A, B=m.B, w=m.w, C=m.C, D=m.D.copy(), e=m.e.copy(),
+                           Q=m.Q, P=m.P, R=m.R, ru=m.ru, u_scale=m.u_scale)
+    bad.e[1, -1] = 3.0                                              # mode 1: -uhat_3 <= 3 instead of <= 1
+    with pytest.raises(ValueError, match='unit box'):
+        bad.validate()

@@ -136,3 +136,38 @@ def test_tstar_against_reference_form_golden(gpu_oracle):
             seen[key] = gpu_oracle._tstar_all(R, Vr)[0].cpu().numpy()
         t = seen[key][g['cand']]
         assert abs(t - g['tstar']) <= 2e-6 * max(1.0, abs(g['tstar'])), (g['cand'], t, g['tstar'])
+
+
+def test_edge_cases_of_the_c_abi(gpu_oracle):
+    """Empty batches are no-ops, bad arguments are error codes (never exceptions inside the library),
+    unsupported problem shapes are refused with a message."""
+    import torch
+    from explicit_hybrid_mpc_b200 import _capi
+    from explicit_hybrid_mpc_b200.mpc_library import HybridMPCProblem, SyntheticMPLP
+    from explicit_hybrid_mpc_b200.oracle import Oracle
+    L, h = _capi.lib(), gpu_oracle._p.handle
+    z = torch.zeros(8, dtype=torch.float64, device='cuda')
+    zi = torch.zeros(8, dtype=torch.int32, device='cuda')
+    assert L.ehm_p_theta_batch(h, 0, z.data_ptr(), zi.data_ptr(), None, None, None, None) == 0
+    assert L.ehm_v_r_batch(h, 0, z.data_ptr(), zi.data_ptr(), None, None, None, None) == 0
+    assert L.ehm_bar_e_batch(h, 0, z.data_ptr(), z.data_ptr(), zi.data_ptr(), None, None) == 0
+    assert L.ehm_qp_theta_delta_batch(h, 0, z.data_ptr(), zi.data_ptr(), z.data_ptr(), None, zi.data_ptr(), None) == 0
+    assert L.ehm_split_batch(4, 0, z.data_ptr(), z.data_ptr(), z.data_ptr(), zi.data_ptr(), None) == 0
+    assert L.ehm_p_theta_batch(h, -1, z.data_ptr(), zi.data_ptr(), None, None, None, None) == _capi.EHM_EINVAL
+    assert L.ehm_bar_d_batch(h, 1, z.data_ptr(), z.data_ptr(), None, zi.data_ptr(), z.data_ptr(), z.data_ptr(),
+                             z.data_ptr(), zi.data_ptr(), None, None) == _capi.EHM_EINVAL
+    assert L.ehm_split_batch(17, 1, z.data_ptr(), z.data_ptr(), z.data_ptr(), zi.data_ptr(), None) == _capi.EHM_EINVAL
+    # a shape without a compiled kernel
+    odd = SyntheticMPLP(n=3, nz=4, rows=6, K=2, seed=1)
+    with pytest.raises(_capi.EhmError, match='no compiled kernel'):
+        Oracle(odd, 0.1, 0.1)
+    # the synthetic n=8 shape is compiled for LP costs only
+    m = SyntheticMPLP()
+    pb = m.problem
+    qp = HybridMPCProblem(n_x=pb.n_x, n_u=pb.n_u, N=1, K=pb.K, A=pb.A, B=pb.B, w=pb.w, C=pb.C, D=pb.D, e=pb.e,
+                          Q=pb.Q, P=pb.P, R=np.eye(pb.n_u), ru=pb.ru, u_scale=pb.u_scale).validate()
+
+    class _M:
+        problem, theta_scale = qp, m.theta_scale
+    with pytest.raises(_capi.EhmError, match='LP costs only'):
+        Oracle(_M(), 0.1, 0.1)
