@@ -242,8 +242,8 @@ def test_eps_a_as_create_oracle_derives_it(pendulum):
 def test_synthetic_mplp_partition_cpu():
     """BASELINE config 5's problem family (synthetic n=8 mp-LP, 4 modes) through the CPU oracle:
     the data generator is well posed (no infeasible region in [-1,1]^8) and the partition of a few
-    Kuhn simplices closes with leaves that tile them.  (Oracle side only: the CUDA engine has no
-    NV = 25 kernel instantiation in round 1.)"""
+    Kuhn simplices closes with leaves that tile them.  (The CUDA engine's run of the same problem is
+    tests/test_gpu_tree_parity.py::test_synthetic_mplp_tree_equals_cpu_oracle.)"""
     from explicit_hybrid_mpc_b200.mpc_library import SyntheticMPLP
     from explicit_hybrid_mpc_b200.tools import kuhn_triangulation, simplex_volume
     from oracle.oracle_cpu import CpuOracle
