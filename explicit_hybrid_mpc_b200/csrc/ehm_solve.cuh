@@ -25,7 +25,9 @@
 //
 // Candidate tables live in global memory (L2 resident: 60 MB for the pendulum), column-major
 // with the row index fastest so that a warp's load of one column is one coalesced 256 B
-// segment per 32 rows.
+// segment per 32 rows.  The candidate's cost matrix M (one contiguous block) is staged by TMA
+// (cp.async.bulk + mbarrier, SASS UBLKCP) behind the row assembly and the phase-1 solve when its size
+// is a multiple of 16 bytes; measured effect: none (profiles/r2_tma_before_after.txt).
 #pragma once
 #include "ehm_ipm.cuh"
 
